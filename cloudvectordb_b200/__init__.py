@@ -1,0 +1,15 @@
+"""B200-native exact nearest-neighbour engine (FAISS-style surface).
+
+    index = IndexFlatIP(d)          # or IndexFlatL2(d); storage="bf16" | "exact"
+    index.add(x)                    # [n, d] float32 / bfloat16, numpy or torch (host or cuda)
+    D, I = index.search(q, k)       # D [nq, k] f32, I [nq, k] i64
+
+Everything numeric runs in hand-written sm_100a kernels behind the C ABI in
+``include/cvdb_b200.h``; this package only moves pointers.
+"""
+from .index import IndexFlat, IndexFlatIP, IndexFlatL2, merge_topk  # noqa: F401
+from .kmeans import Kmeans  # noqa: F401
+from .mining import mine_hard_negatives  # noqa: F401
+from .sharded import ShardedIndex  # noqa: F401
+
+__all__ = ["IndexFlat", "IndexFlatIP", "IndexFlatL2", "merge_topk", "Kmeans", "mine_hard_negatives", "ShardedIndex"]

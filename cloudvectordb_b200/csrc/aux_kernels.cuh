@@ -1,0 +1,255 @@
+// CUDA-core kernels around the fused GEMM+top-k: row packing (fp32/bf16 ->
+// padded bf16 planes, norms), the k-way merges, and the k-means update.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "topk_util.cuh"
+
+namespace cvdb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t other = shfl_xor_u64(v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---------------------------------------------------------------------------
+// pack_rows: one warp per row.
+//   planes == 1 : out[r][0:d] = bf16(x)                       (row width Kp)
+//   planes == 3 : out[r][p*Kp + c] = p-th bf16 piece of x     (x == hi+mid+lo to 24 bits)
+//   L2 metric   : three extra columns right after d in plane 0 carry the norm
+//                 term so that the GEMM itself yields q.x - |x|^2/2:
+//                   database row: bf16 split of -|x|^2/2 ; query row: 1, 1, 1
+//   norms[r] = |x|^2 of the values actually stored (optional).
+// ---------------------------------------------------------------------------
+template <typename Tin>
+__global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, int64_t in_stride,
+                                 __nv_bfloat16* __restrict__ out, int Kp, int planes, int l2, int is_query,
+                                 float* __restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int row_elems = planes * Kp;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const Tin* src = in + r * in_stride;
+        __nv_bfloat16* dst = out + r * row_elems;
+        float nrm = 0.f;
+        for (int c = lane; c < Kp; c += 32) {
+            float x = c < d ? to_f32(src[c]) : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+            // the three norm columns of plane 0 are written by lane 0 below
+            if (!(l2 && c >= d && c < d + 3)) dst[c] = hi;
+            if (planes == 3) {
+                const float r1 = x - __bfloat162float(hi);
+                const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+                const float r2 = r1 - __bfloat162float(mid);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+                dst[Kp + c] = mid;
+                dst[2 * Kp + c] = lo;
+                const float stored = __bfloat162float(hi) + __bfloat162float(mid) + __bfloat162float(lo);
+                nrm = fmaf(stored, stored, nrm);
+            } else {
+                const float stored = __bfloat162float(hi);
+                nrm = fmaf(stored, stored, nrm);
+            }
+        }
+        nrm = warp_sum(nrm);
+        if (lane == 0) {
+            if (norms) norms[r] = nrm;
+            if (l2) {
+                if (is_query) {
+                    const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
+                    dst[d] = one; dst[d + 1] = one; dst[d + 2] = one;
+                } else {
+                    const float t = -0.5f * nrm;
+                    const __nv_bfloat16 a = __float2bfloat16_rn(t);
+                    const float r1 = t - __bfloat162float(a);
+                    const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+                    const float r2 = r1 - __bfloat162float(b);
+                    dst[d] = a; dst[d + 1] = b; dst[d + 2] = __float2bfloat16_rn(r2);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// merge_partials: final k-way select over the per-slice lists of one query
+// (one warp per query), turn keys into (D, I).
+//   IP: D = score.            L2: D = |q|^2 - 2*score (squared distance).
+//   Missing results: I = -1, D = -inf (IP) / +inf (L2).
+// Keys are unique (distinct rows), so "largest key below the previous pick"
+// enumerates the candidates in order.
+// ---------------------------------------------------------------------------
+template <typename Tidx>
+__global__ void merge_partials_kernel(const uint64_t* __restrict__ part, int64_t nq, int n_cand, int k, int l2,
+                                      const float* __restrict__ qnorm, int64_t id_base, float* __restrict__ D,
+                                      Tidx* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const uint64_t* c = part + q * n_cand;
+    uint64_t prev = ~0ull;
+    for (int r = 0; r < k; ++r) {
+        uint64_t best = 0;
+        for (int i = lane; i < n_cand; i += 32) {
+            const uint64_t key = c[i];
+            if (key < prev && key > best) best = key;
+        }
+        best = warp_max_u64(best);
+        if (lane == 0) {
+            if (best == 0) {
+                D[q * k + r] = l2 ? INFINITY : -INFINITY;
+                I[q * k + r] = static_cast<Tidx>(-1);
+            } else {
+                const float s = key_score(best);
+                D[q * k + r] = l2 ? (qnorm[q] - 2.f * s) : s;
+                I[q * k + r] = static_cast<Tidx>(static_cast<int64_t>(key_row(best)) + id_base);
+            }
+        }
+        prev = best ? best : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// merge_lists: k-way select over `nlists` (D, I) result lists per query, as
+// produced by different shards (layout [nlists][nq][k_in]).  Order: better
+// distance first, then lower id; ids < 0 are padding.  One warp per query.
+// ---------------------------------------------------------------------------
+__global__ void merge_lists_kernel(const float* __restrict__ Dc, const int64_t* __restrict__ Ic, int64_t nq, int nlists,
+                                   int k_in, int k, int l2, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const int n_cand = nlists * k_in;
+    // previous pick as (ordered score, id); start above everything
+    uint32_t prev_s = 0xFFFFFFFFu;
+    int64_t prev_id = -1;
+    bool first = true;
+    for (int r = 0; r < k; ++r) {
+        uint32_t bs = 0;
+        int64_t bid = INT64_MAX;
+        bool found = false;
+        for (int i = lane; i < n_cand; i += 32) {
+            const int l = i / k_in, j = i - l * k_in;
+            const int64_t off = (static_cast<int64_t>(l) * nq + q) * k_in + j;
+            const int64_t id = Ic[off];
+            if (id < 0) continue;
+            const float dv = Dc[off];
+            const uint32_t s = float_to_ordered(l2 ? -dv : dv);
+            // strictly after the previous pick in (score desc, id asc) order
+            const bool after = first || s < prev_s || (s == prev_s && id > prev_id);
+            if (!after) continue;
+            if (!found || s > bs || (s == bs && id < bid)) { bs = s; bid = id; found = true; }
+        }
+        // warp argmax on (bs desc, bid asc)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int64_t oid = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(bid), o));
+            const int of = __shfl_xor_sync(0xffffffffu, static_cast<int>(found), o);
+            if (of && (!found || os > bs || (os == bs && oid < bid))) { bs = os; bid = oid; found = true; }
+        }
+        if (lane == 0) {
+            if (!found) {
+                D[q * k + r] = l2 ? INFINITY : -INFINITY;
+                I[q * k + r] = -1;
+            } else {
+                const float s = ordered_to_float(bs);
+                D[q * k + r] = l2 ? -s : s;
+                I[q * k + r] = bid;
+            }
+        }
+        if (!found) {
+            for (int rr = r + 1 + lane; rr < k; rr += 32) {
+                D[q * k + rr] = l2 ? INFINITY : -INFINITY;
+                I[q * k + rr] = -1;
+            }
+            break;
+        }
+        prev_s = bs; prev_id = bid; first = false;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k-means update: sums[assign[i]] += x[i], counts[assign[i]] += 1.
+// One warp per point; fp32 vector reductions at L2 (red.global.add.v4.f32).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename Tin>
+__global__ void kmeans_update_kernel(const Tin* __restrict__ x, int64_t n, int d, const int32_t* __restrict__ assign,
+                                     float* __restrict__ sums, int32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        const int a = assign[i];
+        if (a < 0) continue;
+        const Tin* src = x + i * d;
+        float* dst = sums + static_cast<int64_t>(a) * d;
+        if ((d & 3) == 0) {
+            for (int c = lane * 4; c < d; c += 128)
+                red_add_v4(dst + c, to_f32(src[c]), to_f32(src[c + 1]), to_f32(src[c + 2]), to_f32(src[c + 3]));
+        } else {
+            for (int c = lane; c < d; c += 32) atomicAdd(dst + c, to_f32(src[c]));
+        }
+        if (lane == 0) atomicAdd(counts + a, 1);
+    }
+}
+
+// new centroid = sums / counts where counts > 0, else keep the old centroid
+__global__ void kmeans_finalize_kernel(const float* __restrict__ sums, const int32_t* __restrict__ counts, int K, int d,
+                                       float* __restrict__ centroids) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<int64_t>(K) * d) return;
+    const int c = counts[i / d];
+    if (c > 0) centroids[i] = sums[i] / static_cast<float>(c);
+}
+
+// Exact-mode rescoring: recompute the score of each returned row from the
+// three bf16 planes (their sum reproduces the fp32 value) with fp32 FMAs, so
+// the reported distance does not carry tensor-core accumulation order effects.
+// One warp per (query, rank).
+template <typename Tidx>
+__global__ void rescore_exact_kernel(const __nv_bfloat16* __restrict__ xq, const __nv_bfloat16* __restrict__ xb,
+                                     int64_t nq, int k, int d, int Kp, int l2, int64_t id_base,
+                                     const Tidx* __restrict__ I, float* __restrict__ D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= nq * k) return;
+    const int64_t q = wid / k;
+    const int64_t id = static_cast<int64_t>(I[wid]);
+    if (id < 0) return;
+    const __nv_bfloat16* a = xq + q * 3 * Kp;
+    const __nv_bfloat16* b = xb + (id - id_base) * 3 * Kp;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float av = __bfloat162float(a[c]) + __bfloat162float(a[Kp + c]) + __bfloat162float(a[2 * Kp + c]);
+        const float bv = __bfloat162float(b[c]) + __bfloat162float(b[Kp + c]) + __bfloat162float(b[2 * Kp + c]);
+        if (l2) {
+            const float df = av - bv;
+            acc = fmaf(df, df, acc);
+        } else {
+            acc = fmaf(av, bv, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) D[wid] = acc;
+}
+
+}  // namespace cvdb

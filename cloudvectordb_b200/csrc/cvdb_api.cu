@@ -1,0 +1,672 @@
+// C ABI of the engine (include/cvdb_b200.h): index storage in HBM, query
+// packing, kernel selection and launch, k-way merge.  Host logic only - every
+// arithmetic step runs in the CUDA kernels included below.
+#include "../../include/cvdb_b200.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "aux_kernels.cuh"
+#include "gemm_topk.cuh"
+
+namespace {
+
+using namespace cvdb;
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? CVDB_ENOMEM : CVDB_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+
+#define TRY(expr)                  \
+    do {                           \
+        int r_ = (expr);           \
+        if (r_ != CVDB_OK) return r_; \
+    } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CVDB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) return fail(CVDB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cap = want;
+        return CVDB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() { return static_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D bf16 row-major matrix [rows][row_elems]; box = {64 columns, box_rows}, 128-byte swizzle.
+int make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int row_elems, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(CVDB_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(row_elems) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CVDB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+    return CVDB_OK;
+}
+
+// ------------------------------------------------------------------- index
+struct Index {
+    int d = 0, metric = 0, storage = 0, device = 0;
+    int Kp = 0;         // columns per plane (padded)
+    int planes = 1;     // 1 (bf16) or 3 (exact split)
+    int row_elems = 0;  // planes * Kp
+    int64_t ntotal = 0, capacity = 0;
+    __nv_bfloat16* x = nullptr;
+    int num_sms = 0;
+
+    DevBuf stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
+    bool has_groups = false;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    double last_flops = 0, last_bytes = 0;
+    int last_slices = 0, last_grid = 0;
+};
+
+struct cvdb_guard {
+    int prev = -1;
+    explicit cvdb_guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~cvdb_guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int grow(Index* ix, int64_t need, cudaStream_t st) {
+    if (need <= ix->capacity) return CVDB_OK;
+    int64_t cap = std::max<int64_t>(need, ix->capacity + ix->capacity / 2);
+    cap = std::max<int64_t>(cap, 1024);
+    __nv_bfloat16* nx = nullptr;
+    size_t bytes = static_cast<size_t>(cap) * ix->row_elems * 2;
+    cudaError_t e = cudaMalloc(&nx, bytes);
+    if (e != cudaSuccess && cap > need) {
+        cap = need;
+        bytes = static_cast<size_t>(cap) * ix->row_elems * 2;
+        e = cudaMalloc(&nx, bytes);
+    }
+    if (e != cudaSuccess) return fail(CVDB_ENOMEM, "cudaMalloc(%zu bytes) for %lld rows failed: %s", bytes,
+                                      static_cast<long long>(cap), cudaGetErrorString(e));
+    if (ix->ntotal > 0) {
+        CU_TRY(cudaMemcpyAsync(nx, ix->x, static_cast<size_t>(ix->ntotal) * ix->row_elems * 2, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    if (ix->x) cudaFree(ix->x);
+    ix->x = nx;
+    ix->capacity = cap;
+    return CVDB_OK;
+}
+
+template <typename Tin>
+void launch_pack(const Tin* in, int64_t n, int d, __nv_bfloat16* out, const Index* ix, int is_query, float* norms,
+                 cudaStream_t st) {
+    const int threads = 256;
+    const int64_t blocks = std::min<int64_t>(ceil_div(n, threads / 32), 148 * 32);
+    pack_rows_kernel<Tin><<<static_cast<unsigned>(blocks), threads, 0, st>>>(in, n, d, d, out, ix->Kp, ix->planes,
+                                                                                ix->metric == CVDB_METRIC_L2, is_query, norms);
+    ++g_launches;
+}
+
+int pack_dispatch(const void* in, int dtype, int64_t n, __nv_bfloat16* out, const Index* ix, int is_query, float* norms,
+                  cudaStream_t st) {
+    if (n == 0) return CVDB_OK;
+    if (dtype == CVDB_DTYPE_F32)
+        launch_pack<float>(static_cast<const float*>(in), n, ix->d, out, ix, is_query, norms, st);
+    else
+        launch_pack<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(in), n, ix->d, out, ix, is_query, norms, st);
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+// ------------------------------------------------------- kernel selection
+constexpr int kBlockN = 256;
+constexpr int kStages = 4;
+
+int pick_E(int k) {
+    if (k == 1) return 0;
+    if (k <= 12) return 1;
+    if (k <= 28) return 2;
+    if (k <= 60) return 4;
+    if (k <= 124) return 8;
+    return 16;
+}
+
+// Split the database into slices so that (query tiles x slices) fills the grid
+// in whole waves.  Cost model: waves * (tiles per slice + fixed per-item overhead).
+void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& n_slices, int& tps) {
+    const int ovh = 4;
+    int64_t best = INT64_MAX;
+    n_slices = 1;
+    tps = n_tiles;
+    const int64_t s_max = std::min<int64_t>(std::min<int64_t>(n_tiles, 8LL * grid), std::max<int64_t>(max_slices, 1));
+    for (int64_t s = 1; s <= s_max; ++s) {
+        const int64_t t = ceil_div(n_tiles, s);
+        const int64_t se = ceil_div(n_tiles, t);
+        const int64_t items = se * q_tiles;
+        const int64_t waves = ceil_div(items, grid);
+        const int64_t cost = waves * (t + ovh);
+        if (cost < best) {
+            best = cost;
+            n_slices = static_cast<int>(se);
+            tps = static_cast<int>(t);
+        }
+    }
+}
+
+template <int E>
+int launch_gemm_topk(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid, cudaStream_t st) {
+    auto kern = gemm_topk_ss_kernel<kBlockN, kStages, E>;
+    constexpr size_t smem = gemm_topk_ss_smem_bytes<kBlockN, kStages>();
+    static bool configured = false;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    kern<<<grid, 256, smem, st>>>(tq, tx, p);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+// Core: search `nq` packed-on-the-fly queries against the whole index.
+// Outputs are device pointers: D [nq][k] f32 and either I64 or I32 [nq][k].
+int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, float* D, int64_t* I64, int32_t* I32,
+                  const int32_t* self_ids, const int32_t* group_q, const cvdb_search_opts* opts, cudaStream_t st) {
+    const int E = pick_E(k);
+    const int C = 32 * (E ? E : 1);
+    const int l2 = ix->metric == CVDB_METRIC_L2;
+    const int64_t id_base = opts ? opts->id_base : 0;
+
+    TRY(ix->q_pack.ensure(static_cast<size_t>(nq) * ix->row_elems * 2));
+    TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
+    TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, ix->q_norm.as<float>(), st));
+
+    if (ix->ntotal == 0) {
+        // nothing to search: all padding
+        TRY(ix->part.ensure(static_cast<size_t>(nq) * k * 8));
+        CU_TRY(cudaMemsetAsync(ix->part.p, 0, static_cast<size_t>(nq) * k * 8, st));
+        const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
+        if (I64)
+            merge_partials_kernel<int64_t><<<blocks, 256, 0, st>>>(ix->part.as<uint64_t>(), nq, k, k, l2,
+                                                                   ix->q_norm.as<float>(), id_base, D, I64);
+        else
+            merge_partials_kernel<int32_t><<<blocks, 256, 0, st>>>(ix->part.as<uint64_t>(), nq, k, k, l2,
+                                                                   ix->q_norm.as<float>(), id_base, D, I32);
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+        return CVDB_OK;
+    }
+
+    GemmTopkParams p{};
+    p.nq = static_cast<int>(nq);
+    p.n_rows = static_cast<int>(ix->ntotal);
+    p.k = k;
+    p.q_tiles = static_cast<int>(ceil_div(nq, 128));
+    p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, kBlockN));
+    p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
+    p.plane_cols = ix->Kp;
+    if (ix->planes == 1) {
+        p.n_combo = 1;
+        p.a_planes = p.b_planes = 0;
+    } else {
+        // smallest terms first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
+        p.n_combo = 6;
+        p.a_planes = 0x001102u;  // nibble c = A plane of combo c
+        p.b_planes = 0x010120u;  // nibble c = B plane of combo c
+    }
+    const int sms = ix->num_sms;
+    // keep the per-slice result scratch under ~1 GiB
+    const int64_t max_slices = std::max<int64_t>(1, (int64_t(1) << 30) / std::max<int64_t>(1, nq * k * 8));
+    if (opts && opts->force_slices > 0) {
+        const int64_t s = std::min<int64_t>(opts->force_slices, p.n_tiles);
+        p.tiles_per_slice = static_cast<int>(ceil_div(p.n_tiles, s));
+        p.n_slices = static_cast<int>(ceil_div(p.n_tiles, p.tiles_per_slice));
+    } else {
+        choose_slices(p.q_tiles, p.n_tiles, sms, max_slices, p.n_slices, p.tiles_per_slice);
+    }
+    const int64_t n_items = static_cast<int64_t>(p.q_tiles) * p.n_slices;
+    const int grid = static_cast<int>(std::min<int64_t>(sms, n_items));
+    p.self_ids = self_ids;
+    p.group_q = group_q;
+    p.group_db = (group_q && ix->has_groups) ? ix->groups.as<int32_t>() : nullptr;
+    if (E > 0) TRY(ix->cand.ensure(static_cast<size_t>(grid) * 128 * C * 8));
+    TRY(ix->part.ensure(static_cast<size_t>(nq) * p.n_slices * k * 8));
+    p.cand = ix->cand.as<uint64_t>();
+    p.part = ix->part.as<uint64_t>();
+
+    CUtensorMap tq, tx;
+    TRY(make_tmap_2d(&tq, ix->q_pack.p, nq, ix->row_elems, 128));
+    TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, kBlockN));
+
+    const bool prof = opts && opts->profile;
+    if (prof) {
+        if (!ix->ev0) {
+            CU_TRY(cudaEventCreate(&ix->ev0));
+            CU_TRY(cudaEventCreate(&ix->ev1));
+        }
+        CU_TRY(cudaEventRecord(ix->ev0, st));
+    }
+    switch (E) {
+        case 0: TRY(launch_gemm_topk<0>(tq, tx, p, grid, st)); break;
+        case 1: TRY(launch_gemm_topk<1>(tq, tx, p, grid, st)); break;
+        case 2: TRY(launch_gemm_topk<2>(tq, tx, p, grid, st)); break;
+        case 4: TRY(launch_gemm_topk<4>(tq, tx, p, grid, st)); break;
+        case 8: TRY(launch_gemm_topk<8>(tq, tx, p, grid, st)); break;
+        default: TRY(launch_gemm_topk<16>(tq, tx, p, grid, st)); break;
+    }
+    if (prof) {
+        CU_TRY(cudaEventRecord(ix->ev1, st));
+        ix->ev_valid = true;
+    }
+    ix->last_flops = 2.0 * double(nq) * double(ix->ntotal) * double(ix->d);
+    ix->last_bytes = double(ix->ntotal) * double(ix->row_elems) * 2.0;
+    ix->last_slices = p.n_slices;
+    ix->last_grid = grid;
+
+    const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
+    if (I64)
+        merge_partials_kernel<int64_t><<<blocks, 256, 0, st>>>(p.part, nq, p.n_slices * k, k, l2, ix->q_norm.as<float>(),
+                                                               id_base, D, I64);
+    else
+        merge_partials_kernel<int32_t><<<blocks, 256, 0, st>>>(p.part, nq, p.n_slices * k, k, l2, ix->q_norm.as<float>(),
+                                                               id_base, D, I32);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+
+    if (ix->planes == 3 && D != nullptr) {
+        const unsigned rb = static_cast<unsigned>(ceil_div(nq * k, 8));
+        if (I64)
+            rescore_exact_kernel<int64_t><<<rb, 256, 0, st>>>(ix->q_pack.as<__nv_bfloat16>(), ix->x, nq, k, ix->d, ix->Kp,
+                                                              l2, id_base, I64, D);
+        else
+            rescore_exact_kernel<int32_t><<<rb, 256, 0, st>>>(ix->q_pack.as<__nv_bfloat16>(), ix->x, nq, k, ix->d, ix->Kp,
+                                                              l2, id_base, I32, D);
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+    }
+    return CVDB_OK;
+}
+
+int check_index(cvdb_index_t h) {
+    if (!h) return fail(CVDB_EINVAL, "null index handle");
+    return CVDB_OK;
+}
+
+// queries per launch: bounds the packed-query and result scratch
+int64_t query_chunk(const Index* ix, int k) {
+    const int64_t by_pack = std::max<int64_t>(128, (int64_t(256) << 20) / (int64_t(ix->row_elems) * 2));
+    const int64_t cap = k == 1 ? 262144 : 65536;
+    return std::min(by_pack, cap) / 128 * 128;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+const char* cvdb_last_error(void) { return g_err.c_str(); }
+int64_t cvdb_kernel_launches(void) { return g_launches.load(); }
+int cvdb_version(void) { return 100; }
+
+int cvdb_index_create(int d, int metric, int storage, int device, cvdb_index_t* out) {
+    if (!out) return fail(CVDB_EINVAL, "out is null");
+    *out = nullptr;
+    if (d < 1 || d > 16384) return fail(CVDB_ELIMIT, "d=%d outside [1, 16384]", d);
+    if (metric != CVDB_METRIC_IP && metric != CVDB_METRIC_L2) return fail(CVDB_EINVAL, "unknown metric %d", metric);
+    if (storage != CVDB_STORE_BF16 && storage != CVDB_STORE_EXACT) return fail(CVDB_EINVAL, "unknown storage %d", storage);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CVDB_ECUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(CVDB_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CVDB_ECUDA, "device %d is sm_%d%d; the kernels are built for sm_100a (B200) only", device, prop.major,
+                    prop.minor);
+    Index* ix = new Index();
+    ix->d = d;
+    ix->metric = metric;
+    ix->storage = storage;
+    ix->device = device;
+    ix->planes = storage == CVDB_STORE_EXACT ? 3 : 1;
+    const int extra = metric == CVDB_METRIC_L2 ? 3 : 0;
+    ix->Kp = storage == CVDB_STORE_EXACT ? round_up(d + extra, 64) : round_up(d + extra, 8);
+    ix->row_elems = ix->planes * ix->Kp;
+    ix->num_sms = prop.multiProcessorCount;
+    *out = reinterpret_cast<cvdb_index_t>(ix);
+    return CVDB_OK;
+}
+
+int cvdb_index_destroy(cvdb_index_t h) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    cvdb_guard g(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->x) cudaFree(ix->x);
+    for (DevBuf* b : {&ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
+                      &ix->ids_b, &ix->groups})
+        b->release();
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    delete ix;
+    return CVDB_OK;
+}
+
+int cvdb_index_reset(cvdb_index_t h) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    ix->ntotal = 0;
+    ix->has_groups = false;
+    return CVDB_OK;
+}
+
+int cvdb_index_reserve(cvdb_index_t h, int64_t n) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (n < 0 || n > 0x7FFFFF00LL) return fail(CVDB_ELIMIT, "n=%lld outside [0, 2^31)", static_cast<long long>(n));
+    cvdb_guard g(ix->device);
+    return grow(ix, n, nullptr);
+}
+
+int64_t cvdb_index_ntotal(cvdb_index_t h) { return h ? reinterpret_cast<Index*>(h)->ntotal : -1; }
+int cvdb_index_dim(cvdb_index_t h) { return h ? reinterpret_cast<Index*>(h)->d : -1; }
+
+int cvdb_index_add(cvdb_index_t h, const void* x, int64_t n, int dtype, int on_device, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (n < 0) return fail(CVDB_EINVAL, "n < 0");
+    if (n == 0) return CVDB_OK;
+    if (!x) return fail(CVDB_EINVAL, "x is null");
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (ix->ntotal + n > 0x7FFFFF00LL) return fail(CVDB_ELIMIT, "an index holds fewer than 2^31 rows per GPU");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(grow(ix, ix->ntotal + n, st));
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    __nv_bfloat16* dst = ix->x + ix->ntotal * ix->row_elems;
+    if (on_device) {
+        TRY(pack_dispatch(x, dtype, n, dst, ix, 0, nullptr, st));
+    } else {
+        // stage through a bounded device buffer
+        const int64_t chunk = std::max<int64_t>(1, (int64_t(256) << 20) / (int64_t(ix->d) * esz));
+        TRY(ix->stage_in.ensure(static_cast<size_t>(std::min(chunk, n)) * ix->d * esz));
+        for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+            const int64_t m = std::min(chunk, n - r0);
+            CU_TRY(cudaMemcpyAsync(ix->stage_in.p, static_cast<const char*>(x) + r0 * ix->d * esz,
+                                   static_cast<size_t>(m) * ix->d * esz, cudaMemcpyHostToDevice, st));
+            TRY(pack_dispatch(ix->stage_in.p, dtype, m, dst + r0 * ix->row_elems, ix, 0, nullptr, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    ix->ntotal += n;
+    ix->has_groups = false;
+    return CVDB_OK;
+}
+
+int cvdb_index_set_groups(cvdb_index_t h, const int32_t* group_db, int on_device, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!group_db) {
+        ix->has_groups = false;
+        return CVDB_OK;
+    }
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(ix->groups.ensure(static_cast<size_t>(std::max<int64_t>(ix->ntotal, 1)) * 4));
+    CU_TRY(cudaMemcpyAsync(ix->groups.p, group_db, static_cast<size_t>(ix->ntotal) * 4,
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!on_device) CU_TRY(cudaStreamSynchronize(st));
+    ix->has_groups = true;
+    return CVDB_OK;
+}
+
+int cvdb_index_search(cvdb_index_t h, const void* q, int64_t nq, int dtype, int k, float* D, int64_t* I, int on_device,
+                      const cvdb_search_opts* opts, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
+    if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (nq == 0) return CVDB_OK;
+    if (!q || !D || !I) return fail(CVDB_EINVAL, "q, D and I must be non-null");
+    if (opts && opts->group_q && !ix->has_groups)
+        return fail(CVDB_EINVAL, "group_q given but the index has no groups (cvdb_index_set_groups)");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    const int64_t chunk = query_chunk(ix, k);
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t m = std::min(chunk, nq - q0);
+        const void* qsrc = static_cast<const char*>(q) + q0 * ix->d * esz;
+        const int32_t* self = (opts && opts->self_ids) ? opts->self_ids + q0 : nullptr;
+        const int32_t* grp = (opts && opts->group_q) ? opts->group_q + q0 : nullptr;
+        float* Dd = D + q0 * k;
+        int64_t* Id = I + q0 * k;
+        if (!on_device) {
+            TRY(ix->stage_in.ensure(static_cast<size_t>(m) * ix->d * esz));
+            CU_TRY(cudaMemcpyAsync(ix->stage_in.p, qsrc, static_cast<size_t>(m) * ix->d * esz, cudaMemcpyHostToDevice, st));
+            qsrc = ix->stage_in.p;
+            if (self) {
+                TRY(ix->ids_a.ensure(static_cast<size_t>(m) * 4));
+                CU_TRY(cudaMemcpyAsync(ix->ids_a.p, self, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, st));
+                self = ix->ids_a.as<int32_t>();
+            }
+            if (grp) {
+                TRY(ix->ids_b.ensure(static_cast<size_t>(m) * 4));
+                CU_TRY(cudaMemcpyAsync(ix->ids_b.p, grp, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, st));
+                grp = ix->ids_b.as<int32_t>();
+            }
+            TRY(ix->out_d.ensure(static_cast<size_t>(m) * k * 4));
+            TRY(ix->out_i.ensure(static_cast<size_t>(m) * k * 8));
+            Dd = ix->out_d.as<float>();
+            Id = ix->out_i.as<int64_t>();
+        }
+        TRY(search_device(ix, qsrc, m, dtype, k, Dd, Id, nullptr, self, grp, opts, st));
+        if (!on_device) {
+            CU_TRY(cudaMemcpyAsync(D + q0 * k, Dd, static_cast<size_t>(m) * k * 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(I + q0 * k, Id, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    return CVDB_OK;
+}
+
+int cvdb_index_assign(cvdb_index_t h, const void* x, int64_t n, int dtype, int32_t* assign, float* dist, int on_device,
+                      void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (n < 0) return fail(CVDB_EINVAL, "n < 0");
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (n == 0) return CVDB_OK;
+    if (!x || !assign) return fail(CVDB_EINVAL, "x and assign must be non-null");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    const int64_t chunk = query_chunk(ix, 1);
+    for (int64_t q0 = 0; q0 < n; q0 += chunk) {
+        const int64_t m = std::min(chunk, n - q0);
+        const void* qsrc = static_cast<const char*>(x) + q0 * ix->d * esz;
+        int32_t* Ad = assign + q0;
+        float* Dd = dist ? dist + q0 : nullptr;
+        if (!on_device) {
+            TRY(ix->stage_in.ensure(static_cast<size_t>(m) * ix->d * esz));
+            CU_TRY(cudaMemcpyAsync(ix->stage_in.p, qsrc, static_cast<size_t>(m) * ix->d * esz, cudaMemcpyHostToDevice, st));
+            qsrc = ix->stage_in.p;
+            TRY(ix->out_i.ensure(static_cast<size_t>(m) * 4));
+            Ad = ix->out_i.as<int32_t>();
+        }
+        if (!on_device || !Dd) {
+            TRY(ix->out_d.ensure(static_cast<size_t>(m) * 4));
+            Dd = ix->out_d.as<float>();
+        }
+        TRY(search_device(ix, qsrc, m, dtype, 1, Dd, nullptr, Ad, nullptr, nullptr, nullptr, st));
+        if (!on_device) {
+            CU_TRY(cudaMemcpyAsync(assign + q0, Ad, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost, st));
+            if (dist) CU_TRY(cudaMemcpyAsync(dist + q0, Dd, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    return CVDB_OK;
+}
+
+float cvdb_index_last_kernel_ms(cvdb_index_t h) {
+    if (!h) return -1.f;
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix->ev_valid) return -1.f;
+    cvdb_guard g(ix->device);
+    if (cudaEventSynchronize(ix->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int cvdb_index_last_work(cvdb_index_t h, double* flops, double* db_bytes, int* n_slices, int* grid) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (flops) *flops = ix->last_flops;
+    if (db_bytes) *db_bytes = ix->last_bytes;
+    if (n_slices) *n_slices = ix->last_slices;
+    if (grid) *grid = ix->last_grid;
+    return CVDB_OK;
+}
+
+int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric, float* D,
+                    int64_t* I, int on_device, void* stream) {
+    if (nq < 0 || nlists < 1 || k_in < 1 || k < 1) return fail(CVDB_EINVAL, "bad sizes");
+    if (metric != CVDB_METRIC_IP && metric != CVDB_METRIC_L2) return fail(CVDB_EINVAL, "unknown metric %d", metric);
+    if (nq == 0) return CVDB_OK;
+    if (!Dc || !Ic || !D || !I) return fail(CVDB_EINVAL, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n_in = static_cast<size_t>(nq) * nlists * k_in, n_out = static_cast<size_t>(nq) * k;
+    const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
+    if (on_device) {
+        merge_lists_kernel<<<blocks, 256, 0, st>>>(Dc, Ic, nq, nlists, k_in, k, metric == CVDB_METRIC_L2, D, I);
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+        return CVDB_OK;
+    }
+    void *dDc = nullptr, *dIc = nullptr, *dD = nullptr, *dI = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dDc); cudaFree(dIc); cudaFree(dD); cudaFree(dI);
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&dDc, n_in * 4)) != cudaSuccess || (e = cudaMalloc(&dIc, n_in * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&dD, n_out * 4)) != cudaSuccess || (e = cudaMalloc(&dI, n_out * 8)) != cudaSuccess) {
+        cleanup();
+        return fail(CVDB_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(dDc, Dc, n_in * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dIc, Ic, n_in * 8, cudaMemcpyHostToDevice, st);
+    merge_lists_kernel<<<blocks, 256, 0, st>>>(static_cast<float*>(dDc), static_cast<int64_t*>(dIc), nq, nlists, k_in, k,
+                                               metric == CVDB_METRIC_L2, static_cast<float*>(dD), static_cast<int64_t*>(dI));
+    ++g_launches;
+    cudaMemcpyAsync(D, dD, n_out * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(I, dI, n_out * 8, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(CVDB_ECUDA, "merge failed: %s", cudaGetErrorString(e));
+    return CVDB_OK;
+}
+
+int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int32_t* assign, float* sums,
+                           int32_t* counts, void* stream) {
+    if (n < 0 || d < 1) return fail(CVDB_EINVAL, "bad sizes");
+    if (n == 0) return CVDB_OK;
+    if (!x || !assign || !sums || !counts) return fail(CVDB_EINVAL, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t blocks = std::min<int64_t>(ceil_div(n, 8), 148 * 16);
+    if (dtype == CVDB_DTYPE_F32)
+        kmeans_update_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const float*>(x), n, d,
+                                                                                     assign, sums, counts);
+    else if (dtype == CVDB_DTYPE_BF16)
+        kmeans_update_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), n, d, assign, sums, counts);
+    else
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+int cvdb_kmeans_finalize(const float* sums, const int32_t* counts, int K, int d, float* centroids, void* stream) {
+    if (K < 1 || d < 1) return fail(CVDB_EINVAL, "bad sizes");
+    if (!sums || !counts || !centroids) return fail(CVDB_EINVAL, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t total = static_cast<int64_t>(K) * d;
+    kmeans_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, st>>>(sums, counts, K, d, centroids);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// Candidate keys and the warp-level bitonic network used by the fused top-k
+// epilogue and by the merge kernels.
+//
+// A candidate is one 64-bit key: (orderable(score) << 32) | ~row.  Larger key
+// == better candidate: higher score first, then LOWER row id (the oracle's tie
+// rule).  Key 0 is "no candidate" (it would need row == 0xFFFFFFFF).
+#pragma once
+#include <stdint.h>
+
+namespace cvdb {
+
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+    return (static_cast<uint64_t>(float_to_ordered(score)) << 32) | static_cast<uint32_t>(~row);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_float(static_cast<uint32_t>(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~static_cast<uint32_t>(k); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), mask);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), mask);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+    uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Sort 32*E keys held by one warp into DESCENDING order.  Element p lives in
+// register key[p / 32] of lane p % 32.  Fully unrolled: every register index
+// is a compile-time constant.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&key)[E]) {
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int C = 32 * E;
+#pragma unroll
+    for (int size = 2; size <= C; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < 32) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t other = shfl_xor_u64(key[e], stride);
+                    const uint32_t p = e * 32 + lane;
+                    const bool desc_block = (size == C) || ((p & size) == 0);
+                    const bool first = (lane & stride) == 0;
+                    const bool take_max = (desc_block == first);
+                    const uint64_t mx = key[e] > other ? key[e] : other;
+                    const uint64_t mn = key[e] > other ? other : key[e];
+                    key[e] = take_max ? mx : mn;
+                }
+            } else {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int es = stride >> 5;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & es) == 0) {
+                        const int e2 = e | es;
+                        const bool desc_block = (size == C) || (((e * 32) & size) == 0);
+                        const uint64_t a = key[e], b = key[e2];
+                        const uint64_t mx = a > b ? a : b;
+                        const uint64_t mn = a > b ? b : a;
+                        key[e] = desc_block ? mx : mn;
+                        key[e2] = desc_block ? mn : mx;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// value of element `pos` (0-based, warp-uniform) after the sort, broadcast to all lanes
+template <int E>
+__device__ __forceinline__ uint64_t warp_sorted_at(const uint64_t (&key)[E], int pos) {
+    uint64_t sel = key[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e)
+        if ((pos >> 5) == e) sel = key[e];
+    return shfl_u64(sel, pos & 31);
+}
+#endif  // __CUDACC__
+
+}  // namespace cvdb

@@ -1,0 +1,261 @@
+"""FAISS-style flat index surface over the C ABI (include/cvdb_b200.h).
+
+Mirrors the convention BASELINE.json's north_star fixes for the hot path
+(reference: README.md:2 "building the vectordb" - no reference API exists):
+``IndexFlatIP(d)`` / ``IndexFlatL2(d)``, ``add(x)``, ``search(q, k) -> (D, I)``,
+``ntotal``, ``d``, ``reset()``.
+
+Inputs may be numpy arrays (host buffers: the C ABI does the host<->device
+copies) or torch tensors (cuda tensors are used in place, on the current torch
+stream).  float32 and bfloat16 are accepted.  Outputs come back in the same
+container kind and place as the queries.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _C
+
+try:  # torch is plumbing (device memory, streams); numpy-only use works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Buf:
+    """A [n, d] row-major buffer the C ABI can read: pointer + dtype + place."""
+
+    def __init__(self, x, d: Optional[int] = None, what: str = "x"):
+        if _is_torch(x):
+            if x.dim() == 1 and d is not None:
+                x = x.view(1, -1)
+            if x.dim() != 2:
+                raise ValueError(f"{what} must be 2-D [n, d]")
+            if x.dtype == torch.float32:
+                self.dtype = _C.DTYPE_F32
+            elif x.dtype == torch.bfloat16:
+                self.dtype = _C.DTYPE_BF16
+            else:
+                raise TypeError(f"{what}: dtype {x.dtype} not supported (float32 or bfloat16)")
+            x = x.contiguous()
+            self.on_device = x.is_cuda
+            self.device_index = x.device.index if x.is_cuda else None
+            self.ptr = x.data_ptr()
+            self.kind = "torch"
+        else:
+            x = np.asarray(x)
+            if x.ndim == 1 and d is not None:
+                x = x.reshape(1, -1)
+            if x.ndim != 2:
+                raise ValueError(f"{what} must be 2-D [n, d]")
+            if x.dtype != np.float32:
+                x = x.astype(np.float32)
+            x = np.ascontiguousarray(x)
+            self.dtype = _C.DTYPE_F32
+            self.on_device = False
+            self.device_index = None
+            self.ptr = x.ctypes.data
+            self.kind = "numpy"
+        self.keep = x
+        self.n, self.d = int(x.shape[0]), int(x.shape[1])
+        if d is not None and self.d != d:
+            raise ValueError(f"{what} has d={self.d}, index has d={d}")
+
+
+def _i32_buf(v, n: int, like: _Buf, what: str):
+    """int32 [n] vector living where `like` lives; returns (ptr, keepalive)."""
+    if v is None:
+        return None, None
+    if like.on_device:
+        t = torch.as_tensor(v, dtype=torch.int32, device=f"cuda:{like.device_index}").contiguous()
+        if t.numel() != n:
+            raise ValueError(f"{what} must have {n} entries")
+        return t.data_ptr(), t
+    if _is_torch(v):
+        v = v.detach().cpu().numpy()
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.int32))
+    if a.size != n:
+        raise ValueError(f"{what} must have {n} entries")
+    return a.ctypes.data, a
+
+
+def _stream_for(buf: _Buf) -> int:
+    if buf.on_device:
+        return int(torch.cuda.current_stream(buf.device_index).cuda_stream)
+    return 0
+
+
+class IndexFlat:
+    """Exact (brute-force) index.  ``storage="bf16"`` keeps rows as bf16 and
+    scores with bf16 x bf16 -> fp32 tensor-core MMAs; ``storage="exact"`` keeps
+    a three-way bf16 split of every fp32 value and reproduces fp32 scores."""
+
+    def __init__(self, d: int, metric: str = "ip", storage: str = "bf16", device: int = 0):
+        self._h = C.c_void_p()
+        metric_code = {"ip": _C.METRIC_IP, "l2": _C.METRIC_L2}[metric.lower()]
+        storage_code = {"bf16": _C.STORE_BF16, "exact": _C.STORE_EXACT}[storage.lower()]
+        self.metric = metric.lower()
+        self.storage = storage.lower()
+        self.device = int(device)
+        self._d = int(d)
+        _C.check(_C.lib().cvdb_index_create(int(d), metric_code, storage_code, int(device), C.byref(self._h)))
+
+    # -- FAISS-like members ------------------------------------------------
+    @property
+    def d(self) -> int:
+        return self._d
+
+    @property
+    def ntotal(self) -> int:
+        return int(_C.lib().cvdb_index_ntotal(self._h))
+
+    def reset(self) -> None:
+        _C.check(_C.lib().cvdb_index_reset(self._h))
+
+    def reserve(self, n: int) -> None:
+        _C.check(_C.lib().cvdb_index_reserve(self._h, int(n)))
+
+    def add(self, x) -> None:
+        b = _Buf(x, self._d, "x")
+        self._check_place(b)
+        _C.check(_C.lib().cvdb_index_add(self._h, b.ptr, b.n, b.dtype, int(b.on_device), _stream_for(b)))
+
+    def set_groups(self, group_db) -> None:
+        """Group id per database row; search(..., group_q=) drops same-group rows."""
+        if group_db is None:
+            _C.check(_C.lib().cvdb_index_set_groups(self._h, None, 0, None))
+            return
+        if _is_torch(group_db) and group_db.is_cuda:
+            t = group_db.to(torch.int32).contiguous()
+            if t.numel() != self.ntotal:
+                raise ValueError("group_db must have ntotal entries")
+            _C.check(_C.lib().cvdb_index_set_groups(self._h, t.data_ptr(), 1,
+                                                    int(torch.cuda.current_stream(self.device).cuda_stream)))
+            torch.cuda.current_stream(self.device).synchronize()
+            return
+        if _is_torch(group_db):
+            group_db = group_db.numpy()
+        a = np.ascontiguousarray(np.asarray(group_db, dtype=np.int32))
+        if a.size != self.ntotal:
+            raise ValueError("group_db must have ntotal entries")
+        _C.check(_C.lib().cvdb_index_set_groups(self._h, a.ctypes.data, 0, None))
+
+    def search(self, q, k: int, *, self_ids=None, group_q=None, id_base: int = 0, profile: bool = False,
+               force_slices: int = 0) -> Tuple[object, object]:
+        b = _Buf(q, self._d, "q")
+        self._check_place(b)
+        k = int(k)
+        opts = _C.SearchOpts()
+        sp, keep_s = _i32_buf(self_ids, b.n, b, "self_ids")
+        gp, keep_g = _i32_buf(group_q, b.n, b, "group_q")
+        opts.self_ids = sp
+        opts.group_q = gp
+        opts.id_base = int(id_base)
+        opts.profile = int(profile)
+        opts.force_slices = int(force_slices)
+        if b.on_device:
+            dev = f"cuda:{b.device_index}"
+            D = torch.empty((b.n, k), dtype=torch.float32, device=dev)
+            I = torch.empty((b.n, k), dtype=torch.int64, device=dev)
+            dp, ip = D.data_ptr(), I.data_ptr()
+        else:
+            Dn = np.empty((b.n, k), np.float32)
+            In = np.empty((b.n, k), np.int64)
+            dp, ip = Dn.ctypes.data, In.ctypes.data
+        _C.check(_C.lib().cvdb_index_search(self._h, b.ptr, b.n, b.dtype, k, dp, ip, int(b.on_device), C.byref(opts),
+                                            _stream_for(b)))
+        del keep_s, keep_g
+        if b.on_device:
+            return D, I
+        if b.kind == "torch":
+            return torch.from_numpy(Dn), torch.from_numpy(In)
+        return Dn, In
+
+    def assign(self, x, return_dist: bool = True):
+        """Nearest index row of every x (k = 1): (assign int32 [n], dist f32 [n])."""
+        b = _Buf(x, self._d, "x")
+        self._check_place(b)
+        if b.on_device:
+            dev = f"cuda:{b.device_index}"
+            A = torch.empty((b.n,), dtype=torch.int32, device=dev)
+            Dd = torch.empty((b.n,), dtype=torch.float32, device=dev) if return_dist else None
+            ap, dp = A.data_ptr(), (Dd.data_ptr() if return_dist else None)
+        else:
+            An = np.empty((b.n,), np.int32)
+            Dn = np.empty((b.n,), np.float32) if return_dist else None
+            ap, dp = An.ctypes.data, (Dn.ctypes.data if return_dist else None)
+        _C.check(_C.lib().cvdb_index_assign(self._h, b.ptr, b.n, b.dtype, ap, dp, int(b.on_device), _stream_for(b)))
+        if b.on_device:
+            return A, Dd
+        if b.kind == "torch":
+            return torch.from_numpy(An), (torch.from_numpy(Dn) if return_dist else None)
+        return An, Dn
+
+    # -- measurement hooks ---------------------------------------------------
+    def last_kernel_ms(self) -> float:
+        return float(_C.lib().cvdb_index_last_kernel_ms(self._h))
+
+    def last_work(self) -> dict:
+        f, by, s, g = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        _C.check(_C.lib().cvdb_index_last_work(self._h, C.byref(f), C.byref(by), C.byref(s), C.byref(g)))
+        return {"flops": f.value, "db_bytes": by.value, "n_slices": s.value, "grid": g.value}
+
+    # -- internals -----------------------------------------------------------
+    def _check_place(self, b: _Buf) -> None:
+        if b.on_device and b.device_index != self.device:
+            raise ValueError(f"tensor lives on cuda:{b.device_index}, index on cuda:{self.device}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _C.lib().cvdb_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IndexFlatIP(IndexFlat):
+    def __init__(self, d: int, storage: str = "bf16", device: int = 0):
+        super().__init__(d, "ip", storage, device)
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d: int, storage: str = "bf16", device: int = 0):
+        super().__init__(d, "l2", storage, device)
+
+
+def merge_topk(D_parts, I_parts, k: int, metric: str = "ip"):
+    """k-way select over per-shard results stacked as [nlists, nq, k_in]
+    (numpy -> host path, torch cuda -> device path on the current stream)."""
+    metric_code = {"ip": _C.METRIC_IP, "l2": _C.METRIC_L2}[metric.lower()]
+    if _is_torch(D_parts):
+        Dc = D_parts.to(torch.float32).contiguous()
+        Ic = I_parts.to(torch.int64).contiguous()
+        nl, nq, k_in = Dc.shape
+        if Dc.is_cuda:
+            D = torch.empty((nq, k), dtype=torch.float32, device=Dc.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=Dc.device)
+            _C.check(_C.lib().cvdb_merge_topk(Dc.data_ptr(), Ic.data_ptr(), nq, nl, k_in, int(k), metric_code,
+                                              D.data_ptr(), I.data_ptr(), 1,
+                                              int(torch.cuda.current_stream(Dc.device.index).cuda_stream)))
+            return D, I
+        D, I = merge_topk(Dc.numpy(), Ic.numpy(), k, metric)
+        return torch.from_numpy(D), torch.from_numpy(I)
+    Dc = np.ascontiguousarray(np.asarray(D_parts, np.float32))
+    Ic = np.ascontiguousarray(np.asarray(I_parts, np.int64))
+    nl, nq, k_in = Dc.shape
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    _C.check(_C.lib().cvdb_merge_topk(Dc.ctypes.data, Ic.ctypes.data, nq, nl, k_in, int(k), metric_code, D.ctypes.data,
+                                      I.ctypes.data, 0, None))
+    return D, I

@@ -1,0 +1,96 @@
+"""Shard/merge layer: the database is row-sharded over the ranks of a
+``torch.distributed`` group (one process per GPU); every rank searches its
+shard with the fused kernel, the per-rank (D, I) candidates are exchanged with
+ONE all-gather (NCCL over NVLink) and each rank does the final k-way select.
+
+Top-k over a union of row sets == top-k of the per-set top-k lists, so this is
+the only collective on the path.  Global ids are the
+concatenation of the shards in rank order.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from .index import IndexFlat, merge_topk
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous row range [lo, hi) of `rank` when n rows are split over `world` ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedIndex:
+    def __init__(self, d: int, metric: str = "ip", storage: str = "bf16", device: Optional[int] = None,
+                 group=None, local_index=None, merge_fn: Optional[Callable] = None):
+        """`local_index` / `merge_fn` exist so the host logic can be exercised on CPU
+        (gloo) with stand-ins; the product path builds an IndexFlat on `device`."""
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.d, self.metric, self.storage = int(d), metric.lower(), storage.lower()
+        if local_index is None:
+            if device is None:
+                device = torch.cuda.current_device()
+            local_index = IndexFlat(d, metric, storage, device)
+        self.local = local_index
+        self.merge_fn = merge_fn or merge_topk
+        self.id_base = 0
+        self._ntotal = 0
+        self._counts = [0] * self.world
+
+    # ------------------------------------------------------------------ add
+    def add(self, x) -> None:
+        """x is the SAME full matrix on every rank; each rank keeps its contiguous slice.
+        Only valid on an empty index (global ids stay the row numbers of x)."""
+        if self._ntotal != 0:
+            raise ValueError("add() of a replicated matrix needs an empty index; use add_local() to append shards")
+        lo, hi = shard_bounds(int(x.shape[0]), self.world, self.rank)
+        self.add_local(x[lo:hi])
+
+    def add_local(self, x_shard) -> None:
+        """Every rank appends its own rows; ids are assigned in rank order."""
+        self.local.add(x_shard)
+        n_loc = int(self.local.ntotal)
+        if self.world > 1:
+            counts = [None] * self.world
+            dist.all_gather_object(counts, n_loc, group=self.group)
+        else:
+            counts = [n_loc]
+        self._counts = [int(c) for c in counts]
+        self.id_base = sum(self._counts[: self.rank])
+        self._ntotal = sum(self._counts)
+
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def reset(self) -> None:
+        self.local.reset()
+        self.id_base, self._ntotal, self._counts = 0, 0, [0] * self.world
+
+    def set_groups_local(self, group_shard) -> None:
+        self.local.set_groups(group_shard)
+
+    # --------------------------------------------------------------- search
+    def search(self, q, k: int, *, self_ids=None, group_q=None):
+        """q is replicated on every rank.  self_ids are GLOBAL row ids."""
+        local_self = None
+        if self_ids is not None:
+            s = torch.as_tensor(self_ids).to(torch.int64)
+            in_shard = (s >= self.id_base) & (s < self.id_base + self._counts[self.rank])
+            local_self = torch.where(in_shard, s - self.id_base, torch.full_like(s, -1)).to(torch.int32)
+        D, I = self.local.search(q, k, self_ids=local_self, group_q=group_q, id_base=self.id_base)
+        if self.world == 1:
+            return D, I
+        D = torch.as_tensor(D)
+        I = torch.as_tensor(I)
+        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        return self.merge_fn(Dg, Ig, k, self.metric)

@@ -1,0 +1,123 @@
+/* cvdb_b200.h - C ABI of the B200-native exact nearest-neighbour engine.
+ *
+ * Drop-in boundary for the one data-parallel hot path of a CloudVectorDB-style
+ * pipeline: brute-force inner-product / L2 distance over an embedding matrix,
+ * fused with per-query top-k.
+ *
+ * Reference interface each entry point replaces: the reference
+ * (dorenwick/CloudVectorDB) ships only README.md; README.md:2 names the stages
+ * ("building a very large dataset of triplets", "building the vectordb") whose
+ * inner search this library implements.  There is no reference FFI to mirror,
+ * so the surface follows the FAISS IndexFlat / Kmeans convention that
+ * BASELINE.json's north_star fixes: add() / search(queries, k) -> (D, I).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CVDB_E* code on failure;
+ *     cvdb_last_error() returns the message of the calling thread's last failure.
+ *   - plain pointers and sizes only.  `on_device` says whether ALL data pointers
+ *     of that call (inputs and outputs) are device (1) or host (0) pointers.
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  With device
+ *     pointers a call only enqueues work; with host pointers it returns after
+ *     the outputs have been copied back.
+ *   - rows are C-contiguous [n, d]; ids are insertion order starting at 0.
+ *   - search results: IP sorted by descending score, L2 by ascending SQUARED
+ *     distance, ties broken by lower id; missing results have I = -1 and
+ *     D = -inf (IP) / +inf (L2).
+ *   - one index handle is not thread-safe; distinct handles are.
+ *   - there is no CPU fallback: without a B200-class GPU every compute entry
+ *     point fails with CVDB_ECUDA.
+ */
+#ifndef CVDB_B200_H
+#define CVDB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVDB_OK 0
+#define CVDB_EINVAL (-1)   /* bad argument */
+#define CVDB_ECUDA (-2)    /* CUDA runtime / driver failure, or no usable GPU */
+#define CVDB_ENOMEM (-3)   /* device allocation failed */
+#define CVDB_ELIMIT (-4)   /* argument outside the supported range (k, d) */
+
+#define CVDB_METRIC_IP 0
+#define CVDB_METRIC_L2 1
+
+#define CVDB_DTYPE_F32 0
+#define CVDB_DTYPE_BF16 1
+
+/* how database rows are kept in HBM */
+#define CVDB_STORE_BF16 0  /* one bf16 plane: bf16 x bf16 -> fp32 tensor-core scores */
+#define CVDB_STORE_EXACT 1 /* three bf16 planes (hi+mid+lo == the fp32 value): fp32-fidelity scores */
+
+#define CVDB_MAX_K 504
+
+typedef struct cvdb_index_s* cvdb_index_t;
+
+/* Optional per-search arguments (zero-initialise, then set what is needed).
+ * self_ids / group_q follow the `on_device` flag of the search call. */
+typedef struct cvdb_search_opts {
+    const int32_t* self_ids; /* [nq] database row to exclude for query i (-1: none), or NULL          */
+    const int32_t* group_q;  /* [nq] group id of query i (<0: none); rows of the same group
+                                (see cvdb_index_set_groups) are excluded, or NULL                     */
+    int64_t id_base;         /* added to every returned id (shard offset)                             */
+    int profile;             /* 1: bracket the GEMM+top-k kernel with CUDA events (cvdb_index_last_kernel_ms) */
+    int force_slices;        /* >0: override the database-slice heuristic (testing)                   */
+    int force_variant;       /* 0: auto; otherwise pick a kernel variant (testing)     */
+} cvdb_search_opts;
+
+/* -- index lifetime -------------------------------------------------------
+ * FAISS IndexFlatIP(d) / IndexFlatL2(d) analogue.  `device` is the CUDA ordinal. */
+int cvdb_index_create(int d, int metric, int storage, int device, cvdb_index_t* out);
+int cvdb_index_destroy(cvdb_index_t idx);
+int cvdb_index_reset(cvdb_index_t idx);               /* ntotal = 0, keeps the allocation   */
+int cvdb_index_reserve(cvdb_index_t idx, int64_t n);  /* capacity for n rows in total       */
+int64_t cvdb_index_ntotal(cvdb_index_t idx);
+int cvdb_index_dim(cvdb_index_t idx);
+
+/* FAISS add(x): append n rows (copied; caller keeps ownership of x). */
+int cvdb_index_add(cvdb_index_t idx, const void* x, int64_t n, int dtype, int on_device, void* stream);
+
+/* Group id per database row [ntotal] for positive exclusion in hard-negative
+ * mining (README.md:2 "dataset of triplets"); NULL clears. */
+int cvdb_index_set_groups(cvdb_index_t idx, const int32_t* group_db, int on_device, void* stream);
+
+/* FAISS search(q, k) -> (D [nq,k] f32, I [nq,k] i64). */
+int cvdb_index_search(cvdb_index_t idx, const void* q, int64_t nq, int dtype, int k, float* D, int64_t* I,
+                      int on_device, const cvdb_search_opts* opts, void* stream);
+
+/* k = 1 assignment against the index rows: assign [n] int32 (+id_base not applied), dist [n] f32 or NULL.
+ * Used as the k-means assignment step with the centroids as index rows. */
+int cvdb_index_assign(cvdb_index_t idx, const void* x, int64_t n, int dtype, int32_t* assign, float* dist,
+                      int on_device, void* stream);
+
+/* device time of the last profiled GEMM+top-k kernel (blocks until it finished); <0 if none */
+float cvdb_index_last_kernel_ms(cvdb_index_t idx);
+/* algorithmic work of the last search: flops = 2*nq*ntotal*d*planes_factor, db bytes streamed once */
+int cvdb_index_last_work(cvdb_index_t idx, double* flops, double* db_bytes, int* n_slices, int* grid);
+
+/* -- shard/merge layer ----------------------------------------------------
+ * k-way select over `nlists` per-shard result lists, laid out [nlists][nq][k_in]
+ * (what an all-gather of per-rank (D, I) produces).  Output [nq][k]. */
+int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric,
+                    float* D, int64_t* I, int on_device, void* stream);
+
+/* -- k-means update (IVF coarse quantizer) --------------------------------
+ * sums [K,d] f32 += x[i] for assign[i]; counts [K] i32 += 1.  The caller zeroes
+ * sums/counts and all-reduces them across ranks.  Device pointers only. */
+int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int32_t* assign, float* sums,
+                           int32_t* counts, void* stream);
+/* centroids[j] = sums[j] / counts[j] where counts[j] > 0 (else unchanged).  Device pointers only. */
+int cvdb_kmeans_finalize(const float* sums, const int32_t* counts, int K, int d, float* centroids, void* stream);
+
+/* -- diagnostics ------------------------------------------------------------ */
+const char* cvdb_last_error(void);
+int64_t cvdb_kernel_launches(void); /* kernels launched by this library so far (process-wide) */
+int cvdb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVDB_B200_H */
