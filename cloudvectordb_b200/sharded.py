@@ -33,10 +33,12 @@ class ShardedIndex:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.d, self.metric, self.storage = int(d), metric.lower(), storage.lower()
+        self.device_path = local_index is None
         if local_index is None:
             if device is None:
                 device = torch.cuda.current_device()
             local_index = IndexFlat(d, metric, storage, device)
+        self.device = device
         self.local = local_index
         self.merge_fn = merge_fn or merge_topk
         self.id_base = 0
@@ -77,20 +79,31 @@ class ShardedIndex:
         self.local.set_groups(group_shard)
 
     # --------------------------------------------------------------- search
-    def search(self, q, k: int, *, self_ids=None, group_q=None):
-        """q is replicated on every rank.  self_ids are GLOBAL row ids."""
+    def search(self, q, k: int, *, self_ids=None, group_q=None, profile: bool = False):
+        """q is replicated on every rank.  self_ids are GLOBAL row ids.  Host queries
+        are staged to the rank's GPU (the exchange runs over NCCL) and the merged
+        result is returned on the host."""
+        host_io = False
+        if self.device_path and self.world > 1 and not (isinstance(q, torch.Tensor) and q.is_cuda):
+            host_io = True
+            q = torch.as_tensor(q).to(f"cuda:{self.device}", non_blocking=True)
+        kw = {"profile": profile} if self.device_path else {}
         local_self = None
         if self_ids is not None:
             s = torch.as_tensor(self_ids).to(torch.int64)
             in_shard = (s >= self.id_base) & (s < self.id_base + self._counts[self.rank])
             local_self = torch.where(in_shard, s - self.id_base, torch.full_like(s, -1)).to(torch.int32)
-        D, I = self.local.search(q, k, self_ids=local_self, group_q=group_q, id_base=self.id_base)
+        D, I = self.local.search(q, k, self_ids=local_self, group_q=group_q, id_base=self.id_base, **kw)
         if self.world == 1:
             return D, I
         D = torch.as_tensor(D)
         I = torch.as_tensor(I)
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-        dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
-        return self.merge_fn(Dg, Ig, k, self.metric)
+        # one exchange step: every rank receives every rank's k candidates per query
+        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
+        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
+        Dm, Im = self.merge_fn(Dg, Ig, k, self.metric)
+        if host_io:
+            return Dm.cpu(), Im.cpu()
+        return Dm, Im

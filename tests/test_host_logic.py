@@ -1,0 +1,173 @@
+"""CPU tests for the host side: the C-ABI library loads and exports every
+symbol include/cvdb_b200.h declares, argument validation that needs no GPU,
+the shard arithmetic, and the world_size-2 shard/merge path over gloo with
+oracle-backed stand-ins for the per-rank search."""
+import ctypes as C
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cloudvectordb_b200 import _C
+from cloudvectordb_b200.sharded import ShardedIndex, shard_bounds
+from oracle import flat_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "cvdb_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cvdb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _C.lib()
+    names = header_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cvdb_b200.h but not exported"
+    assert set(names) == set(_C.SIGNATURES), "ctypes signatures and header disagree"
+    assert lib.cvdb_version() >= 100
+    assert lib.cvdb_kernel_launches() >= 0
+
+
+def test_header_constants_match_binding():
+    txt = open(os.path.join(ROOT, "include", "cvdb_b200.h")).read()
+    consts = dict(re.findall(r"#define\s+(CVDB_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", txt))
+    assert int(consts["CVDB_METRIC_L2"]) == _C.METRIC_L2
+    assert int(consts["CVDB_DTYPE_BF16"]) == _C.DTYPE_BF16
+    assert int(consts["CVDB_STORE_EXACT"]) == _C.STORE_EXACT
+    assert int(consts["CVDB_MAX_K"]) == _C.MAX_K
+    assert int(consts["CVDB_ECUDA"]) == _C.ECUDA
+
+
+def test_argument_validation_without_gpu():
+    lib = _C.lib()
+    h = C.c_void_p()
+    assert lib.cvdb_index_create(0, 0, 0, 0, C.byref(h)) == _C.ELIMIT
+    assert b"d=0" in lib.cvdb_last_error()
+    assert lib.cvdb_index_create(8, 7, 0, 0, C.byref(h)) == _C.EINVAL
+    assert lib.cvdb_index_create(8, 0, 9, 0, C.byref(h)) == _C.EINVAL
+    assert lib.cvdb_index_ntotal(None) == -1
+    assert lib.cvdb_index_search(None, None, 1, 0, 1, None, None, 0, None, None) == _C.EINVAL
+    assert lib.cvdb_merge_topk(None, None, 4, 0, 1, 1, 0, None, None, 0, None) == _C.EINVAL
+    if not torch.cuda.is_available():
+        # no CPU fallback: creation must fail loudly without a GPU
+        rc = lib.cvdb_index_create(8, 0, 0, 0, C.byref(h))
+        assert rc == _C.ECUDA and b"no CPU fallback" in lib.cvdb_last_error()
+        with pytest.raises(_C.CvdbError):
+            from cloudvectordb_b200 import IndexFlatIP
+            IndexFlatIP(8)
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 100, 10_000_001):
+        for w in (1, 2, 3, 8):
+            prev = 0
+            for r in range(w):
+                lo, hi = shard_bounds(n, w, r)
+                assert lo == prev and hi >= lo
+                prev = hi
+            assert prev == n
+            sizes = [shard_bounds(n, w, r)[1] - shard_bounds(n, w, r)[0] for r in range(w)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------- gloo, world_size 2
+class OracleLocalIndex:
+    """Stand-in for IndexFlat on CPU ranks: same surface, oracle arithmetic."""
+
+    def __init__(self, d, metric):
+        self.d, self.metric = d, metric
+        self.x = np.zeros((0, d), np.float32)
+        self.groups = None
+
+    @property
+    def ntotal(self):
+        return self.x.shape[0]
+
+    def add(self, x):
+        self.x = np.concatenate([self.x, np.asarray(x, np.float32)])
+
+    def reset(self):
+        self.x = self.x[:0]
+
+    def set_groups(self, g):
+        self.groups = None if g is None else np.asarray(g, np.int32)
+
+    def search(self, q, k, self_ids=None, group_q=None, id_base=0):
+        sid = None if self_ids is None else np.asarray(self_ids, np.int64)
+        D, I = O.search_ref(self.x, np.asarray(q, np.float32), k, O.METRIC_IP if self.metric == "ip" else O.METRIC_L2,
+                            self_ids=sid, group_db=self.groups if group_q is not None else None,
+                            group_q=None if group_q is None else np.asarray(group_q))
+        I = np.where(I >= 0, I + id_base, -1)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def oracle_merge(Dg, Ig, k, metric):
+    Dm, Im = O.merge_ref(list(Dg.numpy()), list(Ig.numpy()), k, O.METRIC_IP if metric == "ip" else O.METRIC_L2)
+    return torch.from_numpy(Dm), torch.from_numpy(Im)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, metric, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        n, d, nq, k = 501, 12, 9, 6
+        xb = rng.standard_normal((n, d), dtype=np.float32)
+        xq = rng.standard_normal((nq, d), dtype=np.float32)
+        groups = (np.arange(n) // 4).astype(np.int32)
+        self_ids = rng.integers(0, n, nq)
+        idx = ShardedIndex(d, metric, local_index=OracleLocalIndex(d, metric), merge_fn=oracle_merge)
+        idx.add(xb)
+        lo, hi = shard_bounds(n, world, rank)
+        assert idx.local.ntotal == hi - lo and idx.id_base == lo and idx.ntotal == n
+        idx.set_groups_local(groups[lo:hi])
+        D, I = idx.search(xq, k)
+        D2, I2 = idx.search(xq, k, self_ids=self_ids, group_q=groups[self_ids])
+        q.put((rank, D.numpy(), I.numpy(), D2.numpy(), I2.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_sharded_search_world2_gloo(metric):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, metric, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(7)
+    n, d, nq, k = 501, 12, 9, 6
+    xb = rng.standard_normal((n, d), dtype=np.float32)
+    xq = rng.standard_normal((nq, d), dtype=np.float32)
+    groups = (np.arange(n) // 4).astype(np.int32)
+    self_ids = rng.integers(0, n, nq)
+    m = O.METRIC_IP if metric == "ip" else O.METRIC_L2
+    D_ref, I_ref = O.search_ref(xb, xq, k, m)
+    D2_ref, I2_ref = O.search_ref(xb, xq, k, m, self_ids=self_ids, group_db=groups, group_q=groups[self_ids])
+    for rank, D, I, D2, I2 in outs:
+        assert np.array_equal(I, I_ref) and np.allclose(D, D_ref, atol=1e-5)
+        assert np.array_equal(I2, I2_ref) and np.allclose(D2, D2_ref, atol=1e-5)

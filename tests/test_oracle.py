@@ -1,0 +1,168 @@
+"""CPU tests: the NumPy oracle against the naive C double loop and the golden
+fixtures.  (The reference has no tests or vectors - README.md only - so these
+pin the oracle itself; DESIGN.md says "parity unpinned".)"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flat_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "flat_small.npz"))
+
+
+def naive_search(lib, xb, xq, k, metric, self_ids=None, group_db=None, group_q=None):
+    xb = np.ascontiguousarray(xb, np.float32)
+    xq = np.ascontiguousarray(xq, np.float32)
+    nq, d = xq.shape
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    sp = gp = gq = None
+    if self_ids is not None:
+        s64 = np.ascontiguousarray(self_ids, np.int64)
+        sp = s64.ctypes.data_as(C.c_void_p)
+    if group_db is not None:
+        gdb = np.ascontiguousarray(group_db, np.int32)
+        gqq = np.ascontiguousarray(group_q, np.int32)
+        gp, gq = gdb.ctypes.data_as(C.c_void_p), gqq.ctypes.data_as(C.c_void_p)
+    lib.naive_search.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.naive_search(xb.ctypes.data, xb.shape[0], xq.ctypes.data, nq, d, k, metric, sp, gp, gq, D.ctypes.data,
+                          I.ctypes.data)
+    assert rc == 0
+    return D, I
+
+
+def rand_unit(rng, n, d):
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("metric", [O.METRIC_IP, O.METRIC_L2])
+@pytest.mark.parametrize("n,d,nq,k", [(64, 8, 5, 3), (300, 17, 9, 10), (50, 4, 3, 50), (10, 6, 4, 16)])
+def test_oracle_matches_naive_loop(naive_lib, metric, n, d, nq, k):
+    rng = np.random.default_rng(n * 31 + d)
+    xb, xq = rand_unit(rng, n, d), rand_unit(rng, nq, d)
+    D, I = O.search_ref(xb, xq, k, metric, block_rows=37)
+    Dn, In = naive_search(naive_lib, xb, xq, k, metric)
+    assert O.check_topk(D, I, Dn, In, tie_tol=1e-5, metric=metric) == 0
+    fin = np.isfinite(Dn)
+    assert np.array_equal(np.isfinite(D), fin)
+    assert np.allclose(D[fin], Dn[fin], atol=2e-6)
+    assert np.array_equal(I < 0, In < 0)
+
+
+def test_tie_rule_lower_id_first(naive_lib):
+    xb = np.zeros((12, 4), np.float32)
+    xb[:, 0] = 1.0                      # every row identical: all scores tie
+    xq = np.array([[1, 0, 0, 0]], np.float32)
+    for metric in (O.METRIC_IP, O.METRIC_L2):
+        D, I = O.search_ref(xb, xq, 5, metric, block_rows=5)
+        assert I.tolist() == [[0, 1, 2, 3, 4]]
+        Dn, In = naive_search(naive_lib, xb, xq, 5, metric)
+        assert In.tolist() == [[0, 1, 2, 3, 4]]
+
+
+def test_padding_when_k_exceeds_n():
+    rng = np.random.default_rng(1)
+    xb, xq = rand_unit(rng, 3, 8), rand_unit(rng, 2, 8)
+    D, I = O.search_ref(xb, xq, 6, O.METRIC_IP)
+    assert (I[:, 3:] == -1).all() and np.isneginf(D[:, 3:]).all()
+    D, I = O.search_ref(xb, xq, 6, O.METRIC_L2)
+    assert (I[:, 3:] == -1).all() and np.isposinf(D[:, 3:]).all()
+    D, I = O.search_ref(np.zeros((0, 8), np.float32), xq, 4, O.METRIC_IP)
+    assert (I == -1).all()
+
+
+def test_l2_is_squared_and_ascending():
+    rng = np.random.default_rng(2)
+    xb, xq = rng.standard_normal((200, 12)).astype(np.float32), rng.standard_normal((7, 12)).astype(np.float32)
+    D, I = O.search_ref(xb, xq, 9, O.METRIC_L2)
+    assert (np.diff(D, axis=1) >= 0).all()
+    direct = ((xq[:, None, :] - xb[I]) ** 2).sum(-1)
+    assert np.allclose(D, direct, rtol=1e-4, atol=1e-4)
+
+
+def test_exclusion_matches_naive(naive_lib):
+    rng = np.random.default_rng(3)
+    n, d, nq, k = 400, 16, 40, 8
+    xb = rand_unit(rng, n, d)
+    self_ids = rng.integers(0, n, nq)
+    xq = xb[self_ids] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32)
+    gdb = (np.arange(n) // 3).astype(np.int32)
+    gq = gdb[self_ids].copy()
+    gq[::3] = -1
+    for metric in (O.METRIC_IP, O.METRIC_L2):
+        D, I = O.search_ref(xb, xq, k, metric, self_ids=self_ids, group_db=gdb, group_q=gq, block_rows=150)
+        Dn, In = naive_search(naive_lib, xb, xq, k, metric, self_ids, gdb, gq)
+        assert O.check_topk(D, I, Dn, In, tie_tol=1e-5, metric=metric) == 0
+        for i in range(nq):
+            assert self_ids[i] not in I[i]
+            if gq[i] >= 0:
+                assert not (gdb[I[i][I[i] >= 0]] == gq[i]).any()
+
+
+def test_golden_fixture_is_reproduced(naive_lib):
+    xb, xq, k = GOLD["xb"], GOLD["xq"], int(GOLD["k"])
+    for name, metric in (("ip", O.METRIC_IP), ("l2", O.METRIC_L2)):
+        D, I = O.search_ref(xb, xq, k, metric)
+        assert np.array_equal(I, GOLD[f"I_{name}"]) and np.allclose(D, GOLD[f"D_{name}"], atol=1e-6)
+        Dn, In = naive_search(naive_lib, xb, xq, k, metric)
+        assert O.check_topk(GOLD[f"D_{name}"], GOLD[f"I_{name}"], Dn, In, tie_tol=1e-5, metric=metric) == 0
+        D, I = O.search_ref(xb, xq, k, metric, self_ids=GOLD["self_ids"], group_db=GOLD["group_db"],
+                            group_q=GOLD["group_q"])
+        assert np.array_equal(I, GOLD[f"I_{name}_excl"])
+    # duplicated rows 7 / 100 / 650 tie for query 3: lower id first
+    assert GOLD["I_ip"][3][:3].tolist() == [7, 100, 650]
+
+
+def test_merge_ref_equals_unsharded():
+    rng = np.random.default_rng(4)
+    xb, xq = rand_unit(rng, 1000, 24), rand_unit(rng, 30, 24)
+    for metric in (O.METRIC_IP, O.METRIC_L2):
+        D, I = O.search_ref(xb, xq, 10, metric)
+        parts = []
+        for lo, hi in ((0, 333), (333, 700), (700, 1000)):
+            Dp, Ip = O.search_ref(xb[lo:hi], xq, 10, metric)
+            parts.append((Dp, np.where(Ip >= 0, Ip + lo, -1)))
+        Dm, Im = O.merge_ref([p[0] for p in parts], [p[1] for p in parts], 10, metric)
+        assert np.array_equal(Im, I) and np.allclose(Dm, D, atol=1e-6)
+
+
+def test_bf16_round_is_rne():
+    x = np.array([1.0, 1.00390625, 1.0 + 2 ** -8 + 2 ** -9, -3.14159, 1e-30, 65504.0], np.float32)
+    r = O.bf16_round(x)
+    assert r[0] == 1.0
+    assert r[1] == 1.0            # exactly half way between 1.0 and 1.0078125: ties to even
+    assert r[2] == np.float32(1.0078125)
+    assert np.all(np.abs(r - x) <= np.abs(x) * 2.0 ** -8)
+    assert np.array_equal(O.bf16_bits_to_f32(O.bf16_bits(x)), r)
+
+
+def test_kmeans_refs(naive_lib):
+    xb, cent = GOLD["xb"], GOLD["km_centroids"]
+    a, dist = O.kmeans_assign_ref(xb, cent, block_rows=97)
+    assert np.array_equal(a, GOLD["km_assign"])
+    n, d = xb.shape
+    an = np.empty(n, np.int32)
+    dn = np.empty(n, np.float32)
+    naive_lib.naive_kmeans_assign.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    naive_lib.naive_kmeans_assign(np.ascontiguousarray(xb).ctypes.data, n, np.ascontiguousarray(cent).ctypes.data,
+                                  cent.shape[0], d, an.ctypes.data, dn.ctypes.data)
+    differ = a != an
+    # a disagreement is only allowed where the two best distances tie
+    assert np.all(np.abs(dist[differ] - dn[differ]) <= 1e-5)
+    assert np.allclose(dist, dn, atol=1e-5)
+    newc, counts, _ = O.kmeans_update_ref(xb, a, cent)
+    assert counts.sum() == n and np.allclose(newc, GOLD["km_new_centroids"], atol=1e-6)
+    j = int(np.argmax(counts))
+    assert np.allclose(newc[j], xb[a == j].mean(0), atol=1e-6)
+
+
+def test_synth_rows_chunk_invariance():
+    a = O.synth_rows(1234, 0, 70000, 8)
+    b = O.synth_rows(1234, 65000, 66000, 8)
+    assert np.array_equal(a[65000:66000], b)
+    assert np.allclose(np.linalg.norm(a[:100], axis=1), 1.0, atol=1e-5)
