@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="database rows of the bounded CPU sample")
     ap.add_argument("--cpu-nq", type=int, default=2048, help="queries of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 streaming kernel, 2 CTA-pair/TMEM kernel")
     return ap.parse_args()
 
 
@@ -201,16 +202,18 @@ def run_ours(a):
     q_host = xq.cpu().pin_memory()
     torch.cuda.synchronize()
 
+    vkw = {"force_variant": a.variant} if (a.variant and world == 1) else {}
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def step_device():
-        return index.search(xq, a.k, profile=True)
+        return index.search(xq, a.k, profile=True, **vkw)
 
     def step_e2e():
-        return index.search(q_host, a.k)
+        return index.search(q_host, a.k, **vkw)
 
     def timed(fn, steps, warmup, collect_kernel=False):
         for _ in range(warmup):
@@ -265,7 +268,7 @@ def run_ours(a):
                 "frac_nominal_2250": achieved / 2250.0, "kernel_ms": kernel_ms,
                 "kernel_share_of_step": kernel_ms / ms_per_step, "flops_per_launch": w["flops"],
                 "db_bytes_per_launch": w["db_bytes"], "hbm_gbs_algorithmic": w["db_bytes"] / kernel_ms / 1e6,
-                "traffic": traffic, "n_slices": w["n_slices"], "grid": w["grid"]}
+                "traffic": traffic, "n_slices": w["n_slices"], "grid": w["grid"], "variant": w["variant"]}
 
     # recall of the bf16 engine against a torch fp32 matmul on a query subsample (rank-local rows -> global merge
     # is already done by the engine, so gather the reference over all ranks' rows)

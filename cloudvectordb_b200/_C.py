@@ -33,6 +33,7 @@ class SearchOpts(C.Structure):
         ("profile", C.c_int),
         ("force_slices", C.c_int),
         ("force_variant", C.c_int),
+        ("debug_flags", C.c_int),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "cvdb_index_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "cvdb_index_last_work": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int)]),
+    "cvdb_index_last_variant": (C.c_int, [C.c_void_p]),
     "cvdb_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_void_p]),
     "cvdb_kmeans_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -120,13 +120,13 @@ struct Index {
     __nv_bfloat16* x = nullptr;
     int num_sms = 0;
 
-    DevBuf stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
+    DevBuf gthr, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
     bool has_groups = false;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     double last_flops = 0, last_bytes = 0;
-    int last_slices = 0, last_grid = 0;
+    int last_slices = 0, last_grid = 0, last_variant = 0;
 };
 
 struct cvdb_guard {
@@ -236,6 +236,35 @@ int launch_gemm_topk(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTop
     return CVDB_OK;
 }
 
+template <int BLOCK_N, int KB_MAX, int STAGES, int E>
+int launch_gemm_topk_ts2(const CUtensorMap& tx, const __nv_bfloat16* q_pack, int q_row_elems, const GemmTopkParams& p,
+                         int grid, cudaStream_t st) {
+    auto kern = gemm_topk_ts2_kernel<BLOCK_N, KB_MAX, STAGES, E>;
+    constexpr size_t smem = gemm_topk_ts2_smem_bytes<BLOCK_N, KB_MAX, STAGES>();
+    static bool configured = false;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    kern<<<grid, 256, smem, st>>>(tx, q_pack, q_row_elems, p);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+template <int BLOCK_N, int KB_MAX, int STAGES>
+int dispatch_ts2(int E, const CUtensorMap& tx, const __nv_bfloat16* q_pack, int q_row_elems, const GemmTopkParams& p,
+                 int grid, cudaStream_t st) {
+    switch (E) {
+        case 0: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 0>(tx, q_pack, q_row_elems, p, grid, st);
+        case 1: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 1>(tx, q_pack, q_row_elems, p, grid, st);
+        case 2: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 2>(tx, q_pack, q_row_elems, p, grid, st);
+        case 4: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 4>(tx, q_pack, q_row_elems, p, grid, st);
+        case 8: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 8>(tx, q_pack, q_row_elems, p, grid, st);
+        default: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 16>(tx, q_pack, q_row_elems, p, grid, st);
+    }
+}
+
 // Core: search `nq` packed-on-the-fly queries against the whole index.
 // Outputs are device pointers: D [nq][k] f32 and either I64 or I32 [nq][k].
 int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, float* D, int64_t* I64, int32_t* I32,
@@ -269,8 +298,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.nq = static_cast<int>(nq);
     p.n_rows = static_cast<int>(ix->ntotal);
     p.k = k;
-    p.q_tiles = static_cast<int>(ceil_div(nq, 128));
-    p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, kBlockN));
+    p.dbg = opts ? opts->debug_flags : 0;
     p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
     p.plane_cols = ix->Kp;
     if (ix->planes == 1) {
@@ -282,7 +310,18 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         p.a_planes = 0x001102u;  // nibble c = A plane of combo c
         p.b_planes = 0x010120u;  // nibble c = B plane of combo c
     }
+    // Kernel variant: 2 = CTA pair with the queries resident in TMEM (one bf16 plane, K <= 768),
+    //                 1 = single-CTA kernel streaming both operands (any K, exact-split storage).
+    int variant = (ix->planes == 1 && p.nkb <= 12) ? 2 : 1;
+    if (opts && opts->force_variant == 1) variant = 1;
+    if (opts && opts->force_variant == 2 && !(ix->planes == 1 && p.nkb <= 12))
+        return fail(CVDB_EINVAL, "variant 2 needs bf16 storage and padded d <= 768");
+    const int block_n = variant == 1 ? kBlockN : (p.nkb <= 8 ? 128 : 64);
+    const int q_tile = variant == 1 ? 128 : 256;
     const int sms = ix->num_sms;
+    const int workers = variant == 1 ? sms : sms / 2;  // CTAs or CTA pairs
+    p.q_tiles = static_cast<int>(ceil_div(nq, q_tile));
+    p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, block_n));
     // keep the per-slice result scratch under ~1 GiB
     const int64_t max_slices = std::max<int64_t>(1, (int64_t(1) << 30) / std::max<int64_t>(1, nq * k * 8));
     if (opts && opts->force_slices > 0) {
@@ -290,10 +329,10 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         p.tiles_per_slice = static_cast<int>(ceil_div(p.n_tiles, s));
         p.n_slices = static_cast<int>(ceil_div(p.n_tiles, p.tiles_per_slice));
     } else {
-        choose_slices(p.q_tiles, p.n_tiles, sms, max_slices, p.n_slices, p.tiles_per_slice);
+        choose_slices(p.q_tiles, p.n_tiles, workers, max_slices, p.n_slices, p.tiles_per_slice);
     }
     const int64_t n_items = static_cast<int64_t>(p.q_tiles) * p.n_slices;
-    const int grid = static_cast<int>(std::min<int64_t>(sms, n_items));
+    const int grid = static_cast<int>(std::min<int64_t>(workers, n_items)) * (variant == 1 ? 1 : 2);
     p.self_ids = self_ids;
     p.group_q = group_q;
     p.group_db = (group_q && ix->has_groups) ? ix->groups.as<int32_t>() : nullptr;
@@ -301,10 +340,13 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     TRY(ix->part.ensure(static_cast<size_t>(nq) * p.n_slices * k * 8));
     p.cand = ix->cand.as<uint64_t>();
     p.part = ix->part.as<uint64_t>();
+    TRY(ix->gthr.ensure(static_cast<size_t>(nq) * 4));
+    CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq) * 4, st));
+    p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
 
     CUtensorMap tq, tx;
-    TRY(make_tmap_2d(&tq, ix->q_pack.p, nq, ix->row_elems, 128));
-    TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, kBlockN));
+    if (variant == 1) TRY(make_tmap_2d(&tq, ix->q_pack.p, nq, ix->row_elems, 128));
+    TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;
     if (prof) {
@@ -314,13 +356,20 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         }
         CU_TRY(cudaEventRecord(ix->ev0, st));
     }
-    switch (E) {
-        case 0: TRY(launch_gemm_topk<0>(tq, tx, p, grid, st)); break;
-        case 1: TRY(launch_gemm_topk<1>(tq, tx, p, grid, st)); break;
-        case 2: TRY(launch_gemm_topk<2>(tq, tx, p, grid, st)); break;
-        case 4: TRY(launch_gemm_topk<4>(tq, tx, p, grid, st)); break;
-        case 8: TRY(launch_gemm_topk<8>(tq, tx, p, grid, st)); break;
-        default: TRY(launch_gemm_topk<16>(tq, tx, p, grid, st)); break;
+    if (variant == 2) {
+        if (block_n == 64)
+            TRY((dispatch_ts2<64, 12, 4>(E, tx, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+        else
+            TRY((dispatch_ts2<128, 8, 3>(E, tx, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+    } else {
+        switch (E) {
+            case 0: TRY(launch_gemm_topk<0>(tq, tx, p, grid, st)); break;
+            case 1: TRY(launch_gemm_topk<1>(tq, tx, p, grid, st)); break;
+            case 2: TRY(launch_gemm_topk<2>(tq, tx, p, grid, st)); break;
+            case 4: TRY(launch_gemm_topk<4>(tq, tx, p, grid, st)); break;
+            case 8: TRY(launch_gemm_topk<8>(tq, tx, p, grid, st)); break;
+            default: TRY(launch_gemm_topk<16>(tq, tx, p, grid, st)); break;
+        }
     }
     if (prof) {
         CU_TRY(cudaEventRecord(ix->ev1, st));
@@ -330,6 +379,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     ix->last_bytes = double(ix->ntotal) * double(ix->row_elems) * 2.0;
     ix->last_slices = p.n_slices;
     ix->last_grid = grid;
+    ix->last_variant = variant;
 
     const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
     if (I64)
@@ -413,7 +463,7 @@ int cvdb_index_destroy(cvdb_index_t h) {
     cvdb_guard g(ix->device);
     cudaDeviceSynchronize();
     if (ix->x) cudaFree(ix->x);
-    for (DevBuf* b : {&ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
+    for (DevBuf* b : {&ix->gthr, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
                       &ix->ids_b, &ix->groups})
         b->release();
     if (ix->ev0) cudaEventDestroy(ix->ev0);
@@ -599,6 +649,8 @@ int cvdb_index_last_work(cvdb_index_t h, double* flops, double* db_bytes, int* n
     if (grid) *grid = ix->last_grid;
     return CVDB_OK;
 }
+
+int cvdb_index_last_variant(cvdb_index_t h) { return h ? reinterpret_cast<Index*>(h)->last_variant : -1; }
 
 int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric, float* D,
                     int64_t* I, int on_device, void* stream) {

@@ -23,6 +23,8 @@
 // writing its sorted top-k to part[query][slice][k]; merge_partials_kernel
 // (select_kernels.cuh) does the final k-way select.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "ptx_sm100.cuh"
 #include "topk_util.cuh"
 
@@ -48,6 +50,8 @@ struct GemmTopkParams {
     const int32_t* group_db;  // [n_rows] group id per database row, or null
     uint64_t* cand;  // [gridDim.x][128][32*E] candidate scratch (E>0)
     uint64_t* part;  // [nq][n_slices][k] per-slice results (keys)
+    uint32_t* gthr;  // [nq] shared per-query threshold (ordered-float), zeroed before the launch
+    int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
 };
 
 // ---------------------------------------------------------------------------
@@ -55,15 +59,35 @@ struct GemmTopkParams {
 // ---------------------------------------------------------------------------
 template <int E>
 struct LaneTopk {
-    float thr;       // score of the current k-th best; -inf until k candidates were seen
+    float thr;       // a score must be strictly greater than this to be a candidate
     int cnt;         // filled slots in buf
     uint64_t* buf;   // 32*E slots, slot p of every query of the warp is zero when p >= cnt
+    uint32_t* gq;    // &gthr[query] (null for padding rows)
 };
 template <>
 struct LaneTopk<0> {
     float thr;
     uint64_t best;
+    uint32_t* gq;
 };
+
+// Threshold sharing between database slices.  gthr[q] holds (as an ordered
+// uint) the k-th best score some slice has already found for query q, i.e. at
+// least k rows score >= it, so any row scoring strictly less can be dropped by
+// every other slice too.  Equal scores must still pass (the tie rule is decided
+// by row id at the merge), hence the "- 1" when adopting a foreign threshold.
+__device__ __forceinline__ float thr_from_shared(uint32_t g) {
+    return g > 1u ? ordered_to_float(g - 1u) : -INFINITY;
+}
+__device__ __forceinline__ float publish_and_refresh(uint32_t* gq, uint64_t kth, float thr) {
+    const uint32_t ord = static_cast<uint32_t>(kth >> 32);  // 0 when fewer than k candidates exist
+    float t = ord ? ordered_to_float(ord) : -INFINITY;      // own k-th: later rows of this slice need strictly more
+    if (gq != nullptr) {
+        const uint32_t old = atomicMax(gq, ord);
+        if (old > ord) t = fmaxf(t, thr_from_shared(old));
+    }
+    return fmaxf(thr, t);
+}
 
 // Sort the buffer of lane `l` (warp-cooperative), keep its best k, zero the rest.
 // Returns the k-th best key (0 when fewer than k candidates exist).
@@ -96,7 +120,7 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
         uint64_t key[E];
         const uint64_t kth = warp_compact<E>(b, k, key);
         if (static_cast<int>(lane) == l) {
-            st.thr = kth ? key_score(kth) : -INFINITY;
+            st.thr = publish_and_refresh(st.gq, kth, st.thr);
             st.cnt = st.cnt < k ? st.cnt : k;
         }
     }
@@ -104,18 +128,27 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
 }
 
 // Process 32 scores (database rows row0 .. row0+31) of this thread's query.
+// Fast path: four independent max-of-8 chains, one vote.  Slow path: only the
+// groups of 8 in which some lane has a candidate are walked element by element.
 template <int E>
 __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0, uint32_t row_end,
                                            uint32_t self, int grp, const int32_t* __restrict__ group_db, int k) {
-    float m = __uint_as_float(v[0]);
+    float m8[4];
 #pragma unroll
-    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    for (int g = 0; g < 4; ++g) {
+        float m = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 3])), __uint_as_float(v[8 * g + 4]));
+        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 5])), __uint_as_float(v[8 * g + 6]));
+        m8[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+    }
+    const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
     if (!__any_sync(0xffffffffu, m > st.thr)) return;  // common case once the threshold has settled
 #pragma unroll
-    for (int g = 0; g < 32; g += 8) {
+    for (int g = 0; g < 4; ++g) {
+        if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
         if constexpr (E > 0) make_room<E>(st, k);
 #pragma unroll
-        for (int j = g; j < g + 8; ++j) {
+        for (int j = 8 * g; j < 8 * g + 8; ++j) {
             const float s = __uint_as_float(v[j]);
             if (s > st.thr) {
                 const uint32_t row = row0 + j;
@@ -131,6 +164,50 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
                 }
             }
         }
+    }
+}
+
+// Start of a work item: reset the selection state of this thread's query.
+template <int E>
+__device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams& p, int q_row, bool q_valid,
+                                           uint64_t* warp_buf) {
+    constexpr int C = 32 * (E > 0 ? E : 1);
+    const uint32_t lane = threadIdx.x & 31;
+    st.gq = (q_valid && p.gthr != nullptr) ? p.gthr + q_row : nullptr;
+    st.thr = st.gq ? thr_from_shared(__ldcg(st.gq)) : -INFINITY;
+    if constexpr (E > 0) {
+        st.cnt = 0;
+        for (int i = lane; i < 32 * C; i += 32) warp_buf[i] = 0;  // the warp's 32 buffers are contiguous
+        __syncwarp();
+    } else {
+        st.best = 0;
+    }
+}
+
+// End of a work item: sorted top-k of every query of the warp -> part[q][slice][0..k).
+template <int E>
+__device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams& p, int q_base, int q_row, bool q_valid,
+                                           int slice) {
+    const uint32_t lane = threadIdx.x & 31;
+    if constexpr (E > 0) {
+        __syncwarp();
+        for (int l = 0; l < 32; ++l) {
+            const int qr = q_base + l;
+            if (qr >= p.nq) break;
+            uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
+            uint64_t key[E];
+            const uint64_t kth = warp_compact<E>(b, p.k, key);
+            if (static_cast<int>(lane) == l && kth != 0 && st.gq != nullptr) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
+            uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pos = e * 32 + lane;
+                if (pos < p.k) out[pos] = key[e];
+            }
+        }
+        __syncwarp();
+    } else {
+        if (q_valid) p.part[static_cast<size_t>(q_row) * p.n_slices + slice] = st.best;
     }
 }
 
@@ -189,50 +266,51 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int ksteps = p.nkb * p.n_combo;
 
     if (warp == 0) {
-        // ------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-                const int t0 = slice * p.tiles_per_slice;
-                const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-                for (int t = t0; t < t1; ++t) {
-                    for (int c = 0; c < p.n_combo; ++c) {
-                        const int a_col = static_cast<int>((p.a_planes >> (4 * c)) & 0xF) * p.plane_cols;
-                        const int b_col = static_cast<int>((p.b_planes >> (4 * c)) & 0xF) * p.plane_cols;
-                        for (int kb = 0; kb < p.nkb; ++kb) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ------------------------------------------------------ TMA producer (warp-uniform loop)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
+            const int t0 = slice * p.tiles_per_slice;
+            const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            for (int t = t0; t < t1; ++t) {
+                for (int c = 0; c < p.n_combo; ++c) {
+                    const int a_col = static_cast<int>((p.a_planes >> (4 * c)) & 0xF) * p.plane_cols;
+                    const int b_col = static_cast<int>((p.b_planes >> (4 * c)) & 0xF) * p.plane_cols;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (elect_one_sync()) {
                             mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
                             tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES, a_col + kb * BLOCK_K,
                                         qt * BLOCK_M, kEvictLast);
                             tma_load_2d(&tmap_x, &full_bar[stage], smem_b + stage * B_BYTES, b_col + kb * BLOCK_K,
                                         t * BLOCK_N, kEvictNormal);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // -------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const int slice = w / p.q_tiles;
-                const int t0 = slice * p.tiles_per_slice;
-                const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-                for (int t = t0; t < t1; ++t) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        // -------------------------------------------------------- MMA issuer (warp-uniform loop)
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int slice = w / p.q_tiles;
+            const int t0 = slice * p.tiles_per_slice;
+            const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int s = 0; s < ksteps; ++s) {
+                    mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                    for (int s = 0; s < ksteps; ++s) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
+                    if (elect_one_sync()) {
                         const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
                         const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
 #pragma unroll
@@ -241,12 +319,13 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
                         }
                         umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (s == ksteps - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
                     }
-                    umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
@@ -255,6 +334,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t lane_base = static_cast<uint32_t>(ewarp * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const int dbg = p.dbg;
         LaneTopk<E> st;
         if constexpr (E > 0)
             st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32 + lane) * C;
@@ -266,16 +346,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const bool q_valid = q_row < p.nq;
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
-            st.thr = -INFINITY;
-            if constexpr (E > 0) {
-                st.cnt = 0;
-                // zero the 32 buffers of this warp (contiguous: 32*C slots)
-                uint64_t* wb = p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C;
-                for (int i = lane; i < 32 * C; i += 32) wb[i] = 0;
-                __syncwarp();
-            } else {
-                st.best = 0;
-            }
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C);
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -284,38 +355,22 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 32) {
                     uint32_t v[32];
-                    tmem_ld32(taddr + c, v);
-                    tmem_ld_wait();
+                    if (!(dbg & 2)) {
+                        tmem_ld32(taddr + c, v);
+                        tmem_ld_wait();
+                    }
                     if (c + 32 == BLOCK_N) {
                         // all of this thread's scores are in registers: hand the accumulator back
                         tc_fence_before();
                         mbar_arrive(&tmem_empty[acc]);
                     }
-                    scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
+                    if (!(dbg & 3))
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            // ---- flush this item's result: part[q][slice][0..k)
-            if constexpr (E > 0) {
-                __syncwarp();
-                for (int l = 0; l < 32; ++l) {
-                    const int qr = qt * BLOCK_M + ewarp * 32 + l;
-                    if (qr >= p.nq) break;
-                    uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
-                    uint64_t key[E];
-                    warp_compact<E>(b, p.k, key);
-                    uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int pos = e * 32 + lane;
-                        if (pos < p.k) out[pos] = key[e];
-                    }
-                }
-                __syncwarp();
-            } else {
-                if (q_valid) p.part[static_cast<size_t>(q_row) * p.n_slices + slice] = st.best;
-            }
+            item_flush<E>(st, p, qt * BLOCK_M + ewarp * 32, q_row, q_valid, slice);
         }
     }
 
@@ -327,6 +382,215 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 template <int BLOCK_N, int STAGES>
 constexpr size_t gemm_topk_ss_smem_bytes() {
     return 1024 /*align slack*/ + size_t(STAGES) * (128 * 64 * 2 + BLOCK_N * 64 * 2) + (2 * STAGES + 4) * 8 + 16;
+}
+
+// ===========================================================================
+// Flagship variant: CTA pair (cta_group::2), queries resident in TMEM.
+//
+//   * a cluster of two CTAs (one SM pair) owns 256 queries; each CTA keeps its
+//     128 query rows in TENSOR MEMORY (bf16 pairs, 32 columns per 64-wide K
+//     block) for the whole work item, so the A operand is never re-read from
+//     shared memory or L2,
+//   * only database rows stream: per tile each CTA TMA-loads half of the
+//     BLOCK_N rows (all K blocks = one pipeline stage), the MMA
+//     (tcgen05.mma.cta_group::2, M = 256) reads both halves,
+//   * accumulators: two buffers of BLOCK_N fp32 columns after the A region
+//     (A 384 + 2 x 64 columns for K <= 768, A 256 + 2 x 128 for K <= 512),
+//   * the epilogue is the same threshold filter, one thread per query row.
+//
+// L2 -> SM traffic per SM is a third of the streaming (SS) kernel's and shared
+// memory is read at a third of its rate, which is what the power-capped B200
+// needs to hold its clocks.
+// ===========================================================================
+template <int BLOCK_N, int KB_MAX, int STAGES, int E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ q_pack,
+                     const int q_row_elems, const GemmTopkParams p) {
+    constexpr int HALF_N = BLOCK_N / 2;                  // database rows this CTA loads per tile
+    constexpr uint32_t KB_BYTES = HALF_N * 128;          // one 64-wide K block of those rows
+    constexpr uint32_t STAGE_BYTES = KB_MAX * KB_BYTES;  // one tile, all K blocks
+    constexpr uint32_t A_COLS = KB_MAX * 32;             // TMEM columns holding the query tile
+    static_assert(A_COLS + 2 * BLOCK_N == 512, "TMEM budget: queries + two accumulators = 512 columns");
+    constexpr int C = 32 * (E > 0 ? E : 1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_b = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                     // leader CTA's copy is the live one
+    uint64_t* empty_bar = bars + STAGES;           // per CTA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // per CTA
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // leader's copy
+    uint64_t* a_ready = bars + 2 * STAGES + 4;     // leader's copy
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();       // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) prefetch_tmap(&tmap_x);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        mbar_init(a_ready, 8);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<2>(tmem_slot, 512);
+        tmem_relinquish<2>();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = p.q_tiles * p.n_slices;  // q_tiles counts 256-query tiles here
+    const int nkb = p.nkb;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer (both CTAs, warp-uniform loop)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const int slice = w / p.q_tiles;
+            const int t0 = slice * p.tiles_per_slice;
+            const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one_sync()) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * nkb * KB_BYTES);
+                    uint8_t* dst = smem_b + stage * STAGE_BYTES;
+                    const int row = t * BLOCK_N + static_cast<int>(rank) * HALF_N;
+                    for (int kb = 0; kb < nkb; ++kb)
+                        tma_load_2d_2sm(&tmap_x, &full_bar[stage], dst + kb * KB_BYTES, kb * 64, row, kEvictNormal);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer (leader only, warp-uniform loop)
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0, item_phase = 0;
+            for (int w = pair; w < n_items; w += n_pairs) {
+                const int slice = w / p.q_tiles;
+                const int t0 = slice * p.tiles_per_slice;
+                const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+                mbar_wait(a_ready, item_phase);  // both CTAs have written their query rows to TMEM
+                item_phase ^= 1;
+                tc_fence_after();
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t tmem_d = tmem_base + A_COLS + acc * BLOCK_N;
+                        const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b + stage * STAGE_BYTES));
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((kb * KB_BYTES) >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_ts<2>(tmem_d, tmem_base + kb * 32 + kk * 8, b_desc + 2 * kk, idesc, (kb | kk) != 0);
+                        }
+                        umma_commit_2sm(&empty_bar[stage], 3);  // frees the stage in both CTAs
+                        umma_commit_2sm(&tmem_full[acc], 3);    // accumulator ready in both CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ----------------------------------------------------------- epilogue (both CTAs)
+        const int ewarp = warp - 4;
+        const uint32_t lane_base = static_cast<uint32_t>(ewarp * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int dbg = p.dbg;
+        LaneTopk<E> st;
+        if constexpr (E > 0)
+            st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32 + lane) * C;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
+            const int t0 = slice * p.tiles_per_slice;
+            const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            const int q_base = qt * 256 + static_cast<int>(rank) * 128 + ewarp * 32;
+            const int q_row = q_base + lane;
+            const bool q_valid = q_row < p.nq;
+            // ---- (1) this thread's query row -> TMEM lane (bf16 pairs, 16 columns per store).
+            // Safe to overwrite: the previous item's last accumulator was consumed, so all
+            // MMAs that read the old rows have retired.
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(q_pack + static_cast<size_t>(q_valid ? q_row : 0) * q_row_elems);
+                const int n_vec = q_valid ? (min(q_row_elems, nkb * 64) >> 3) : 0;  // 16-byte granules with data
+                for (int c16 = 0; c16 < nkb * 2; ++c16) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int vi = c16 * 4 + v;
+                        uint4 x = make_uint4(0, 0, 0, 0);
+                        if (vi < n_vec) x = __ldg(src + vi);
+                        r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                    }
+                    tmem_st16(tmem_base + lane_base + c16 * 16, r);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(a_ready, 0);
+            }
+            const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
+            const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
+                const uint32_t taddr = tmem_base + lane_base + A_COLS + acc * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    if (!(dbg & 2)) {
+                        tmem_ld32(taddr + c, v);
+                        tmem_ld_wait();
+                    }
+                    if (c + 32 == BLOCK_N) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                    }
+                    if (!(dbg & 3))
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal it
+    if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+template <int BLOCK_N, int KB_MAX, int STAGES>
+constexpr size_t gemm_topk_ts2_smem_bytes() {
+    return 1024 + size_t(STAGES) * KB_MAX * (BLOCK_N / 2) * 128 + (2 * STAGES + 6) * 8 + 16;
 }
 
 }  // namespace cvdb

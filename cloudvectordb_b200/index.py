@@ -148,7 +148,7 @@ class IndexFlat:
         _C.check(_C.lib().cvdb_index_set_groups(self._h, a.ctypes.data, 0, None))
 
     def search(self, q, k: int, *, self_ids=None, group_q=None, id_base: int = 0, profile: bool = False,
-               force_slices: int = 0) -> Tuple[object, object]:
+               force_slices: int = 0, force_variant: int = 0, debug_flags: int = 0) -> Tuple[object, object]:
         b = _Buf(q, self._d, "q")
         self._check_place(b)
         k = int(k)
@@ -160,6 +160,8 @@ class IndexFlat:
         opts.id_base = int(id_base)
         opts.profile = int(profile)
         opts.force_slices = int(force_slices)
+        opts.force_variant = int(force_variant)
+        opts.debug_flags = int(debug_flags)
         if b.on_device:
             dev = f"cuda:{b.device_index}"
             D = torch.empty((b.n, k), dtype=torch.float32, device=dev)
@@ -205,7 +207,8 @@ class IndexFlat:
     def last_work(self) -> dict:
         f, by, s, g = C.c_double(), C.c_double(), C.c_int(), C.c_int()
         _C.check(_C.lib().cvdb_index_last_work(self._h, C.byref(f), C.byref(by), C.byref(s), C.byref(g)))
-        return {"flops": f.value, "db_bytes": by.value, "n_slices": s.value, "grid": g.value}
+        return {"flops": f.value, "db_bytes": by.value, "n_slices": s.value, "grid": g.value,
+                "variant": int(_C.lib().cvdb_index_last_variant(self._h))}
 
     # -- internals -----------------------------------------------------------
     def _check_place(self, b: _Buf) -> None:

@@ -39,7 +39,8 @@ def unit_rows(rng, n, d):
     return x
 
 
-def parity_case(name, n, d, nq, k, metric="ip", storage="bf16", excl=False, force_slices=0, seed=0, device_io=False):
+def parity_case(name, n, d, nq, k, metric="ip", storage="bf16", excl=False, force_slices=0, seed=0, device_io=False,
+                variant=0):
     rng = np.random.default_rng(seed)
     xb = unit_rows(rng, n, d)
     xq = unit_rows(rng, nq, d)
@@ -62,14 +63,16 @@ def parity_case(name, n, d, nq, k, metric="ip", storage="bf16", excl=False, forc
             if excl:
                 idx.set_groups(group_db)
             D, I = idx.search(torch.from_numpy(xq).cuda(), k, self_ids=self_ids, group_q=group_q,
-                              force_slices=force_slices)
+                              force_slices=force_slices, force_variant=variant)
             torch.cuda.synchronize()
             D, I = D.cpu().numpy(), I.cpu().numpy()
         else:
             idx.add(xb)
             if excl:
                 idx.set_groups(group_db)
-            D, I = idx.search(xq, k, self_ids=self_ids, group_q=group_q, force_slices=force_slices)
+            D, I = idx.search(xq, k, self_ids=self_ids, group_q=group_q, force_slices=force_slices,
+                              force_variant=variant)
+        used = idx.last_work()["variant"]
     finally:
         idx.close()
     tol = 2e-5 if storage == "bf16" else 1e-5
@@ -79,13 +82,13 @@ def parity_case(name, n, d, nq, k, metric="ip", storage="bf16", excl=False, forc
     inf_mismatch = int((np.isfinite(D_ref) != np.isfinite(D)).sum())
     rec = O.recall_at_k(I, I_ref)
     ok = bad == 0 and inf_mismatch == 0 and maxerr < 1e-3
-    emit(case=name, ok=bool(ok), n=n, d=d, nq=nq, k=k, metric=metric, storage=storage, excl=excl,
+    emit(case=name, ok=bool(ok), variant=used, n=n, d=d, nq=nq, k=k, metric=metric, storage=storage, excl=excl,
          force_slices=force_slices, bad=bad, inf_mismatch=inf_mismatch, maxerr=maxerr, recall=rec,
          idx_equal=float((I == I_ref).mean()), oracle_s=round(t_ref, 3))
     return ok
 
 
-def perf_case(name, n, d, nq, k, metric="ip", iters=3, check_q=64):
+def perf_case(name, n, d, nq, k, metric="ip", iters=3, check_q=64, variant=0, dbg=0):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(1234)
     xb = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
@@ -104,7 +107,7 @@ def perf_case(name, n, d, nq, k, metric="ip", iters=3, check_q=64):
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
             t0.record()
-            D, I = idx.search(xq, k, profile=True)
+            D, I = idx.search(xq, k, profile=True, force_variant=variant, debug_flags=dbg)
             t1.record()
             torch.cuda.synchronize()
             if it > 0:
@@ -132,8 +135,8 @@ def perf_case(name, n, d, nq, k, metric="ip", iters=3, check_q=64):
         derr = float((D[:check_q] - ref_d).abs().max())
         ms = float(np.median(times))
         kms_med = float(np.median(kms))
-        emit(case=name, n=n, d=d, nq=nq, k=k, metric=metric, ms_search=ms, ms_kernel=kms_med,
-             qps=nq / ms * 1e3, tflops_kernel=w["flops"] / kms_med / 1e9, n_slices=w["n_slices"], grid=w["grid"],
+        emit(case=name, dbg=dbg, n=n, d=d, nq=nq, k=k, metric=metric, ms_search=ms, ms_kernel=kms_med,
+             qps=nq / ms * 1e3, tflops_kernel=w["flops"] / kms_med / 1e9, n_slices=w["n_slices"], grid=w["grid"], variant=w["variant"],
              recall_vs_torch=rec, max_d_err=derr)
     finally:
         idx.close()
@@ -147,6 +150,9 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--perf", action="store_true")
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--dbg", type=int, default=0)
+    ap.add_argument("--only", default="", help="comma list of perf case names; skips parity")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "check.log"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -175,6 +181,10 @@ def main():
             dict(name="c1_exact", n=100000, d=384, nq=2000, k=10, storage="exact"),
             dict(name="mid_bf16", n=200000, d=768, nq=1000, k=10),
         ]
+    if a.variant:
+        cases = [dict(c, variant=a.variant) for c in cases if c.get("storage", "bf16") == "bf16" or a.variant == 1]
+    if a.only:
+        cases = []
     n_ok = 0
     for c in cases:
         try:
@@ -187,11 +197,18 @@ def main():
     emit(event="parity_done", ok=n_ok, total=len(cases))
     if a.perf:
         try:
-            perf_case("perf_1M", 1_000_000, 768, 10000, 10)
-            perf_case("perf_1M_l2", 1_000_000, 768, 10000, 10, metric="l2")
-            perf_case("perf_small_batch", 4_000_000, 768, 64, 10)
+            v = a.variant
+            pc = [("perf_1M", (1_000_000, 768, 10000, 10), {}),
+                  ("perf_1M_l2", (1_000_000, 765, 10000, 10), dict(metric="l2")),
+                  ("perf_1M_d384_k1", (1_000_000, 384, 100000, 1), dict(metric="l2")),
+                  ("perf_1M_d512", (1_000_000, 512, 10000, 10), {}),
+                  ("perf_small_batch", (4_000_000, 768, 64, 10), {})]
             if a.big:
-                perf_case("perf_10M", 10_000_000, 768, 10000, 10)
+                pc.append(("perf_10M", (10_000_000, 768, 10000, 10), {}))
+            for nm, args, kw in pc:
+                if a.only and nm not in a.only.split(","):
+                    continue
+                perf_case(nm, *args, variant=v, dbg=a.dbg, **kw)
         except Exception as e:
             emit(case="perf", ok=False, error=repr(e), tb=traceback.format_exc()[-800:])
     emit(event="done")
