@@ -236,6 +236,21 @@ int launch_gemm_topk(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTop
     return CVDB_OK;
 }
 
+template <int E>
+int launch_gemm_topk_ss2(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid, cudaStream_t st) {
+    auto kern = gemm_topk_ss2_kernel<256, 6, E>;
+    constexpr size_t smem = gemm_topk_ss2_smem_bytes<256, 6>();
+    static bool configured = false;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    kern<<<grid, 256, smem, st>>>(tq, tx, p);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
 template <int BLOCK_N, int KB_MAX, int STAGES, int E>
 int launch_gemm_topk_ts2(const CUtensorMap& tx, const __nv_bfloat16* q_pack, int q_row_elems, const GemmTopkParams& p,
                          int grid, cudaStream_t st) {
@@ -310,13 +325,21 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         p.a_planes = 0x001102u;  // nibble c = A plane of combo c
         p.b_planes = 0x010120u;  // nibble c = B plane of combo c
     }
-    // Kernel variant: 2 = CTA pair with the queries resident in TMEM (one bf16 plane, K <= 768),
-    //                 1 = single-CTA kernel streaming both operands (any K, exact-split storage).
-    int variant = (ix->planes == 1 && p.nkb <= 12) ? 2 : 1;
+    // Kernel variant (measured on B200, see DESIGN.md "variant selection"):
+    //   1 = single-CTA kernel streaming both operands (any K, any storage): best under the
+    //       power cap for K > 512 and for small (HBM-bound) batches,
+    //   2 = CTA pair with the queries resident in TMEM (bf16 storage, padded K <= 768):
+    //       best for K <= 512 (N = 128 accumulators) and large batches,
+    //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage).
+    const bool ts2_ok = ix->planes == 1 && p.nkb <= 12;
+    int variant = (ts2_ok && p.nkb <= 8 && nq > 256) ? 2 : 1;
     if (opts && opts->force_variant == 1) variant = 1;
-    if (opts && opts->force_variant == 2 && !(ix->planes == 1 && p.nkb <= 12))
-        return fail(CVDB_EINVAL, "variant 2 needs bf16 storage and padded d <= 768");
-    const int block_n = variant == 1 ? kBlockN : (p.nkb <= 8 ? 128 : 64);
+    if (opts && opts->force_variant == 3) variant = 3;
+    if (opts && opts->force_variant == 2) {
+        if (!ts2_ok) return fail(CVDB_EINVAL, "variant 2 needs bf16 storage and padded d <= 768");
+        variant = 2;
+    }
+    const int block_n = variant != 2 ? kBlockN : (p.nkb <= 8 ? 128 : 64);
     const int q_tile = variant == 1 ? 128 : 256;
     const int sms = ix->num_sms;
     const int workers = variant == 1 ? sms : sms / 2;  // CTAs or CTA pairs
@@ -345,7 +368,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
 
     CUtensorMap tq, tx;
-    if (variant == 1) TRY(make_tmap_2d(&tq, ix->q_pack.p, nq, ix->row_elems, 128));
+    if (variant != 2) TRY(make_tmap_2d(&tq, ix->q_pack.p, nq, ix->row_elems, 128));
     TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;
@@ -361,6 +384,15 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
             TRY((dispatch_ts2<64, 12, 4>(E, tx, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
         else
             TRY((dispatch_ts2<128, 8, 3>(E, tx, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+    } else if (variant == 3) {
+        switch (E) {
+            case 0: TRY(launch_gemm_topk_ss2<0>(tq, tx, p, grid, st)); break;
+            case 1: TRY(launch_gemm_topk_ss2<1>(tq, tx, p, grid, st)); break;
+            case 2: TRY(launch_gemm_topk_ss2<2>(tq, tx, p, grid, st)); break;
+            case 4: TRY(launch_gemm_topk_ss2<4>(tq, tx, p, grid, st)); break;
+            case 8: TRY(launch_gemm_topk_ss2<8>(tq, tx, p, grid, st)); break;
+            default: TRY(launch_gemm_topk_ss2<16>(tq, tx, p, grid, st)); break;
+        }
     } else {
         switch (E) {
             case 0: TRY(launch_gemm_topk<0>(tq, tx, p, grid, st)); break;

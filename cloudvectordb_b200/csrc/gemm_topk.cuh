@@ -588,6 +588,192 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
     if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
 }
 
+// ===========================================================================
+// CTA-pair streaming variant (cta_group::2, M = 256, N = BLOCK_N): both
+// operands stream through shared memory in 64-wide K blocks like the
+// single-CTA kernel, but one MMA covers 256 queries, so every database tile is
+// fetched from L2 once per 256 queries and each CTA stages (and the tensor core
+// reads from its shared memory) only half of the B tile.  Any K, any number of
+// plane combos (exact split storage included).
+// ===========================================================================
+template <int BLOCK_N, int STAGES, int E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                     const GemmTopkParams p) {
+    constexpr int BLOCK_K = 64;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr uint32_t A_BYTES = 128 * BLOCK_K * 2;     // this CTA's 128 query rows
+    constexpr uint32_t B_BYTES = HALF_N * BLOCK_K * 2;  // this CTA's half of the database tile
+    static_assert(2 * BLOCK_N <= 512, "two accumulators must fit TMEM");
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr int C = 32 * (E > 0 ? E : 1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t* full_bar = bars;                     // leader's copy is live
+    uint64_t* empty_bar = bars + STAGES;           // per CTA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // per CTA
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // leader's copy
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<2>(tmem_slot, TMEM_COLS);
+        tmem_relinquish<2>();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = p.q_tiles * p.n_slices;  // q_tiles counts 256-query tiles
+    const int ksteps = p.nkb * p.n_combo;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer (both CTAs)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
+            const int t0 = slice * p.tiles_per_slice;
+            const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            const int q_row0 = qt * 256 + static_cast<int>(rank) * 128;
+            for (int t = t0; t < t1; ++t) {
+                const int x_row0 = t * BLOCK_N + static_cast<int>(rank) * HALF_N;
+                for (int c = 0; c < p.n_combo; ++c) {
+                    const int a_col = static_cast<int>((p.a_planes >> (4 * c)) & 0xF) * p.plane_cols;
+                    const int b_col = static_cast<int>((p.b_planes >> (4 * c)) & 0xF) * p.plane_cols;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (elect_one_sync()) {
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (A_BYTES + B_BYTES));
+                            tma_load_2d_2sm(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES, a_col + kb * BLOCK_K,
+                                            q_row0, kEvictLast);
+                            tma_load_2d_2sm(&tmap_x, &full_bar[stage], smem_b + stage * B_BYTES, b_col + kb * BLOCK_K,
+                                            x_row0, kEvictNormal);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer (leader only)
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = pair; w < n_items; w += n_pairs) {
+                const int slice = w / p.q_tiles;
+                const int t0 = slice * p.tiles_per_slice;
+                const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                    for (int s = 0; s < ksteps; ++s) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
+                            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+#pragma unroll
+                            for (int kk = 0; kk < BLOCK_K / 16; ++kk)
+                                umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                            umma_commit_2sm(&empty_bar[stage], 3);
+                            if (s == ksteps - 1) umma_commit_2sm(&tmem_full[acc], 3);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ----------------------------------------------------------- epilogue (both CTAs)
+        const int ewarp = warp - 4;
+        const uint32_t lane_base = static_cast<uint32_t>(ewarp * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int dbg = p.dbg;
+        LaneTopk<E> st;
+        if constexpr (E > 0)
+            st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32 + lane) * C;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
+            const int t0 = slice * p.tiles_per_slice;
+            const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            const int q_base = qt * 256 + static_cast<int>(rank) * 128 + ewarp * 32;
+            const int q_row = q_base + lane;
+            const bool q_valid = q_row < p.nq;
+            const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
+            const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
+                const uint32_t taddr = tmem_base + lane_base + acc * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    if (!(dbg & 2)) {
+                        tmem_ld32(taddr + c, v);
+                        tmem_ld_wait();
+                    }
+                    if (c + 32 == BLOCK_N) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                    }
+                    if (!(dbg & 3))
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<2>(tmem_base, TMEM_COLS);
+}
+
+template <int BLOCK_N, int STAGES>
+constexpr size_t gemm_topk_ss2_smem_bytes() {
+    return 1024 + size_t(STAGES) * (128 * 64 * 2 + (BLOCK_N / 2) * 64 * 2) + (2 * STAGES + 5) * 8 + 16;
+}
+
 template <int BLOCK_N, int KB_MAX, int STAGES>
 constexpr size_t gemm_topk_ts2_smem_bytes() {
     return 1024 + size_t(STAGES) * KB_MAX * (BLOCK_N / 2) * 128 + (2 * STAGES + 6) * 8 + 16;

@@ -1,0 +1,68 @@
+"""torchrun worker for tests/test_gpu_sharded.py: sharded search over NCCL must
+equal the single-GPU search bit for bit (the merge is pure selection)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cloudvectordb_b200 import IndexFlat, Kmeans, ShardedIndex  # noqa: E402
+from cloudvectordb_b200.sharded import shard_bounds  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    n, d, nq, k = 300_001, 256, 777, 10
+    xb = torch.nn.functional.normalize(torch.randn((n, d), generator=g), dim=1).bfloat16()
+    xq = torch.nn.functional.normalize(torch.randn((nq, d), generator=g), dim=1).bfloat16()
+    groups = (torch.arange(n) // 4).to(torch.int32)
+    self_ids = torch.randint(0, n, (nq,), generator=g)
+    for metric in ("ip", "l2"):
+        full = IndexFlat(d, metric, "bf16", device=local)
+        full.add(xb.to(dev))
+        full.set_groups(groups)
+        D_ref, I_ref = full.search(xq.to(dev), k)
+        D2_ref, I2_ref = full.search(xq.to(dev), k, self_ids=self_ids, group_q=groups[self_ids])
+        full.close()
+        sh = ShardedIndex(d, metric, "bf16", device=local)
+        sh.add(xb.to(dev))
+        lo, hi = shard_bounds(n, world, rank)
+        assert sh.local.ntotal == hi - lo and sh.ntotal == n
+        sh.set_groups_local(groups[lo:hi])
+        D, I = sh.search(xq.to(dev), k)
+        assert torch.equal(I, I_ref) and torch.equal(D, D_ref), f"{metric}: sharded != single GPU"
+        D2, I2 = sh.search(xq.to(dev), k, self_ids=self_ids, group_q=groups[self_ids].to(dev))
+        assert torch.equal(I2, I2_ref) and torch.equal(D2, D2_ref), f"{metric}: sharded exclusion != single GPU"
+        Dh, Ih = sh.search(xq, k)                          # host queries -> host results
+        assert not Dh.is_cuda and torch.equal(Ih, I_ref.cpu())
+    # k-means: sharded points, all-reduced update == single-rank update on all points
+    pts = torch.nn.functional.normalize(torch.randn((40_000, 64), generator=g), dim=1).bfloat16()
+    cent = pts[:128].float()
+    km1 = Kmeans(64, 128, niter=1, device=local)
+    km1.centroids = cent.clone().to(dev)
+    dist_group = dist.new_group(ranks=[rank])            # single-rank group: no reduction across ranks
+    km1.group = dist_group
+    km1.step(pts.to(dev))
+    lo, hi = shard_bounds(pts.shape[0], world, rank)
+    km2 = Kmeans(64, 128, niter=1, device=local)
+    km2.centroids = cent.clone().to(dev)
+    km2.step(pts[lo:hi].to(dev))
+    assert torch.equal(km1.last_counts, km2.last_counts)
+    assert torch.allclose(km1.centroids, km2.centroids, rtol=1e-4, atol=1e-6)
+    dist.barrier()
+    if rank == 0:
+        print("SHARDED_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

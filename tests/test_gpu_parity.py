@@ -73,6 +73,52 @@ def test_bf16_kernel_matches_oracle_on_rounded_inputs(metric, n, d, nq, k):
     assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5)
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("metric,n,d,nq,k", [
+    ("ip", 5000, 768, 300, 10),    # K = 768: 64-column accumulators in the TMEM-resident variant
+    ("l2", 7000, 384, 513, 1),     # K <= 512: 128-column accumulators, top-1 path
+    ("ip", 3000, 100, 64, 50),
+    ("l2", 300, 20, 5, 7),         # tiny: the peer CTA of a pair sees only out-of-bounds rows
+    ("ip", 40000, 256, 700, 10),   # several slices and query tiles: shared thresholds in play
+])
+def test_every_kernel_variant_matches_oracle(variant, metric, n, d, nq, k):
+    rng = np.random.default_rng(variant * 1000 + n)
+    xb, xq = O.bf16_round(unit_rows(rng, n, d)), O.bf16_round(unit_rows(rng, nq, d))
+    D_ref, I_ref = O.search_ref(xb, xq, k, M[metric])
+    idx = make_index(d, metric, "bf16")
+    idx.add(xb)
+    D, I = idx.search(xq, k, force_variant=variant)
+    assert idx.last_work()["variant"] == variant
+    idx.close()
+    assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5)
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_exact_storage_on_both_streaming_variants(variant):
+    rng = np.random.default_rng(77)
+    n, d, nq, k = 12000, 200, 150, 10
+    xb, xq = unit_rows(rng, n, d), unit_rows(rng, nq, d)
+    D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_IP)
+    idx = make_index(d, "ip", "exact")
+    idx.add(xb)
+    D, I = idx.search(xq, k, force_variant=variant)
+    idx.close()
+    assert_parity(D, I, D_ref, I_ref, "ip", tie_tol=1e-5, dtol=1e-5)
+
+
+def test_threshold_sharing_is_result_neutral():
+    """debug flag 4 turns the cross-slice threshold sharing off: same answer either way."""
+    rng = np.random.default_rng(78)
+    n, d, nq, k = 60000, 64, 300, 10
+    xb, xq = O.bf16_round(unit_rows(rng, n, d)), O.bf16_round(unit_rows(rng, nq, d))
+    idx = make_index(d, "ip", "bf16")
+    idx.add(xb)
+    D0, I0 = idx.search(xq, k, force_slices=16)
+    D1, I1 = idx.search(xq, k, force_slices=16, debug_flags=4)
+    idx.close()
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+
+
 @pytest.mark.parametrize("slices", [2, 3, 7, 40])
 def test_database_slices_do_not_change_results(slices):
     rng = np.random.default_rng(slices)

@@ -182,7 +182,7 @@ def main():
             dict(name="mid_bf16", n=200000, d=768, nq=1000, k=10),
         ]
     if a.variant:
-        cases = [dict(c, variant=a.variant) for c in cases if c.get("storage", "bf16") == "bf16" or a.variant == 1]
+        cases = [dict(c, variant=a.variant) for c in cases if c.get("storage", "bf16") == "bf16" or a.variant in (1, 3)]
     if a.only:
         cases = []
     n_ok = 0
