@@ -52,6 +52,7 @@ SIGNATURES = {
     "cvdb_index_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p]),
     "cvdb_index_last_kernel_ms": (C.c_float, [C.c_void_p]),
+    "cvdb_index_profile_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "cvdb_index_last_work": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int)]),
     "cvdb_index_last_variant": (C.c_int, [C.c_void_p]),

@@ -123,8 +123,11 @@ struct Index {
     DevBuf gthr, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
     bool has_groups = false;
 
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    // ring of event pairs bracketing profiled GEMM+top-k launches (opts.profile)
+    static constexpr int kProfSlots = 64;
+    cudaEvent_t ev0[kProfSlots] = {}, ev1[kProfSlots] = {};
+    int prof_head = 0;   // next slot to use
+    int prof_count = 0;  // recorded and not yet read (<= kProfSlots)
     double last_flops = 0, last_bytes = 0;
     int last_slices = 0, last_grid = 0, last_variant = 0;
 };
@@ -372,12 +375,13 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;
+    const int slot = ix->prof_head;
     if (prof) {
-        if (!ix->ev0) {
-            CU_TRY(cudaEventCreate(&ix->ev0));
-            CU_TRY(cudaEventCreate(&ix->ev1));
+        if (!ix->ev0[slot]) {
+            CU_TRY(cudaEventCreate(&ix->ev0[slot]));
+            CU_TRY(cudaEventCreate(&ix->ev1[slot]));
         }
-        CU_TRY(cudaEventRecord(ix->ev0, st));
+        CU_TRY(cudaEventRecord(ix->ev0[slot], st));
     }
     if (variant == 2) {
         if (block_n == 64)
@@ -404,8 +408,9 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         }
     }
     if (prof) {
-        CU_TRY(cudaEventRecord(ix->ev1, st));
-        ix->ev_valid = true;
+        CU_TRY(cudaEventRecord(ix->ev1[slot], st));
+        ix->prof_head = (slot + 1) % Index::kProfSlots;
+        ix->prof_count = std::min(ix->prof_count + 1, Index::kProfSlots);
     }
     ix->last_flops = 2.0 * double(nq) * double(ix->ntotal) * double(ix->d);
     ix->last_bytes = double(ix->ntotal) * double(ix->row_elems) * 2.0;
@@ -498,8 +503,10 @@ int cvdb_index_destroy(cvdb_index_t h) {
     for (DevBuf* b : {&ix->gthr, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
                       &ix->ids_b, &ix->groups})
         b->release();
-    if (ix->ev0) cudaEventDestroy(ix->ev0);
-    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    for (int i = 0; i < Index::kProfSlots; ++i) {
+        if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
+        if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
+    }
     delete ix;
     return CVDB_OK;
 }
@@ -661,14 +668,31 @@ int cvdb_index_assign(cvdb_index_t h, const void* x, int64_t n, int dtype, int32
     return CVDB_OK;
 }
 
+int cvdb_index_profile_ms(cvdb_index_t h, float* out_ms, int max_n) {
+    if (!h || !out_ms || max_n < 0) return fail(CVDB_EINVAL, "bad arguments");
+    Index* ix = reinterpret_cast<Index*>(h);
+    cvdb_guard g(ix->device);
+    const int n = std::min(ix->prof_count, max_n);
+    // oldest first
+    for (int i = 0; i < n; ++i) {
+        const int slot = ((ix->prof_head - ix->prof_count + i) % Index::kProfSlots + Index::kProfSlots) % Index::kProfSlots;
+        if (cudaEventSynchronize(ix->ev1[slot]) != cudaSuccess ||
+            cudaEventElapsedTime(&out_ms[i], ix->ev0[slot], ix->ev1[slot]) != cudaSuccess)
+            return fail(CVDB_ECUDA, "profiling events could not be read");
+    }
+    ix->prof_count = 0;
+    return n;
+}
+
 float cvdb_index_last_kernel_ms(cvdb_index_t h) {
     if (!h) return -1.f;
     Index* ix = reinterpret_cast<Index*>(h);
-    if (!ix->ev_valid) return -1.f;
+    if (ix->prof_count < 1) return -1.f;
     cvdb_guard g(ix->device);
-    if (cudaEventSynchronize(ix->ev1) != cudaSuccess) return -1.f;
+    const int slot = (ix->prof_head - 1 + Index::kProfSlots) % Index::kProfSlots;
+    if (cudaEventSynchronize(ix->ev1[slot]) != cudaSuccess) return -1.f;
     float ms = -1.f;
-    if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, ix->ev0[slot], ix->ev1[slot]) != cudaSuccess) return -1.f;
     return ms;
 }
 

@@ -204,6 +204,14 @@ class IndexFlat:
     def last_kernel_ms(self) -> float:
         return float(_C.lib().cvdb_index_last_kernel_ms(self._h))
 
+    def profile_ms(self) -> list:
+        """Device times (ms) of the profiled kernel launches since the previous call."""
+        buf = (C.c_float * 64)()
+        n = _C.lib().cvdb_index_profile_ms(self._h, buf, 64)
+        if n < 0:
+            _C.check(n)
+        return [float(buf[i]) for i in range(n)]
+
     def last_work(self) -> dict:
         f, by, s, g = C.c_double(), C.c_double(), C.c_int(), C.c_int()
         _C.check(_C.lib().cvdb_index_last_work(self._h, C.byref(f), C.byref(by), C.byref(s), C.byref(g)))

@@ -97,6 +97,9 @@ int cvdb_index_assign(cvdb_index_t idx, const void* x, int64_t n, int dtype, int
 
 /* device time of the last profiled GEMM+top-k kernel (blocks until it finished); <0 if none */
 float cvdb_index_last_kernel_ms(cvdb_index_t idx);
+/* device times (ms) of the profiled GEMM+top-k launches since the previous call, oldest first (at most the
+ * last 64); blocks until they finished.  Returns how many were written to out_ms, or a negative error. */
+int cvdb_index_profile_ms(cvdb_index_t idx, float* out_ms, int max_n);
 /* algorithmic work of the last search: flops = 2*nq*ntotal*d*planes_factor, db bytes streamed once */
 int cvdb_index_last_work(cvdb_index_t idx, double* flops, double* db_bytes, int* n_slices, int* grid);
 /* kernel variant the last search used: 1 = single-CTA streaming kernel, 2 = CTA-pair kernel with
