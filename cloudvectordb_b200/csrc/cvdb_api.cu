@@ -254,32 +254,33 @@ int launch_gemm_topk_ss2(const CUtensorMap& tq, const CUtensorMap& tx, const Gem
     return CVDB_OK;
 }
 
-template <int BLOCK_N, int KB_MAX, int STAGES, int E>
-int launch_gemm_topk_ts2(const CUtensorMap& tx, const __nv_bfloat16* q_pack, int q_row_elems, const GemmTopkParams& p,
-                         int grid, cudaStream_t st) {
-    auto kern = gemm_topk_ts2_kernel<BLOCK_N, KB_MAX, STAGES, E>;
-    constexpr size_t smem = gemm_topk_ts2_smem_bytes<BLOCK_N, KB_MAX, STAGES>();
+template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES, int E>
+int launch_gemm_topk_ts2(const CUtensorMap& tx, const CUtensorMap& tq, const __nv_bfloat16* q_pack, int q_row_elems,
+                         const GemmTopkParams& p, int grid, cudaStream_t st) {
+    auto kern = gemm_topk_ts2_kernel<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, E>;
+    constexpr size_t smem = gemm_topk_ts2_smem_bytes<BLOCK_N, KB_S, KB_STAGE, STAGES>();
+    static_assert(smem <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = true;
     }
-    kern<<<grid, 256, smem, st>>>(tx, q_pack, q_row_elems, p);
+    kern<<<grid, 256, smem, st>>>(tx, tq, q_pack, q_row_elems, p);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return CVDB_OK;
 }
 
-template <int BLOCK_N, int KB_MAX, int STAGES>
-int dispatch_ts2(int E, const CUtensorMap& tx, const __nv_bfloat16* q_pack, int q_row_elems, const GemmTopkParams& p,
-                 int grid, cudaStream_t st) {
+template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES>
+int dispatch_ts2(int E, const CUtensorMap& tx, const CUtensorMap& tq, const __nv_bfloat16* q_pack, int q_row_elems,
+                 const GemmTopkParams& p, int grid, cudaStream_t st) {
     switch (E) {
-        case 0: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 0>(tx, q_pack, q_row_elems, p, grid, st);
-        case 1: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 1>(tx, q_pack, q_row_elems, p, grid, st);
-        case 2: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 2>(tx, q_pack, q_row_elems, p, grid, st);
-        case 4: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 4>(tx, q_pack, q_row_elems, p, grid, st);
-        case 8: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 8>(tx, q_pack, q_row_elems, p, grid, st);
-        default: return launch_gemm_topk_ts2<BLOCK_N, KB_MAX, STAGES, 16>(tx, q_pack, q_row_elems, p, grid, st);
+        case 0: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 0>(tx, tq, q_pack, q_row_elems, p, grid, st);
+        case 1: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 1>(tx, tq, q_pack, q_row_elems, p, grid, st);
+        case 2: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 2>(tx, tq, q_pack, q_row_elems, p, grid, st);
+        case 4: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 4>(tx, tq, q_pack, q_row_elems, p, grid, st);
+        case 8: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 8>(tx, tq, q_pack, q_row_elems, p, grid, st);
+        default: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 16>(tx, tq, q_pack, q_row_elems, p, grid, st);
     }
 }
 
@@ -292,9 +293,15 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     const int l2 = ix->metric == CVDB_METRIC_L2;
     const int64_t id_base = opts ? opts->id_base : 0;
 
-    TRY(ix->q_pack.ensure(static_cast<size_t>(nq) * ix->row_elems * 2));
+    // the packed query matrix is padded with zero rows to a whole 256-query tile, so the A-operand
+    // TMA boxes never run out of bounds (partially out-of-bounds boxes load measurably slower)
+    const int64_t nq_pad = ceil_div(nq, 256) * 256;
+    TRY(ix->q_pack.ensure(static_cast<size_t>(nq_pad) * ix->row_elems * 2));
     TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
     TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, ix->q_norm.as<float>(), st));
+    if (nq_pad > nq)
+        CU_TRY(cudaMemsetAsync(ix->q_pack.as<__nv_bfloat16>() + nq * ix->row_elems, 0,
+                               static_cast<size_t>(nq_pad - nq) * ix->row_elems * 2, st));
 
     if (ix->ntotal == 0) {
         // nothing to search: all padding
@@ -329,20 +336,26 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         p.b_planes = 0x010120u;  // nibble c = B plane of combo c
     }
     // Kernel variant (measured on B200, see DESIGN.md "variant selection"):
-    //   1 = single-CTA kernel streaming both operands (any K, any storage): best under the
-    //       power cap for K > 512 and for small (HBM-bound) batches,
-    //   2 = CTA pair with the queries resident in TMEM (bf16 storage, padded K <= 768):
-    //       best for K <= 512 (N = 128 accumulators) and large batches,
-    //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage).
+    //   1 = single-CTA kernel streaming both operands (any K, any storage): small (HBM-bound)
+    //       batches, exact-split storage, K > 768,
+    //   2 = CTA pair with the queries resident on chip (bf16 storage, padded K <= 768; TMEM for the
+    //       first 512 of K, shared-memory tail beyond; 128-column accumulators): large batches,
+    //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage),
+    //   4 = CTA pair with all of K <= 768 in TMEM and 64-column accumulators (comparison only).
     const bool ts2_ok = ix->planes == 1 && p.nkb <= 12;
-    int variant = (ts2_ok && p.nkb <= 8 && nq > 256) ? 2 : 1;
+    int variant = (ts2_ok && nq > 256) ? 2 : 1;
     if (opts && opts->force_variant == 1) variant = 1;
     if (opts && opts->force_variant == 3) variant = 3;
     if (opts && opts->force_variant == 2) {
         if (!ts2_ok) return fail(CVDB_EINVAL, "variant 2 needs bf16 storage and padded d <= 768");
         variant = 2;
     }
-    const int block_n = variant != 2 ? kBlockN : (p.nkb <= 8 ? 128 : 64);
+    if (opts && opts->force_variant == 4) {
+        if (!ts2_ok) return fail(CVDB_EINVAL, "variant 4 needs bf16 storage and padded d <= 768");
+        variant = 4;
+    }
+    const bool resident = variant == 2 || variant == 4;
+    const int block_n = !resident ? kBlockN : (variant == 4 ? 64 : 128);
     const int q_tile = variant == 1 ? 128 : 256;
     const int sms = ix->num_sms;
     const int workers = variant == 1 ? sms : sms / 2;  // CTAs or CTA pairs
@@ -371,7 +384,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
 
     CUtensorMap tq, tx;
-    if (variant != 2) TRY(make_tmap_2d(&tq, ix->q_pack.p, nq, ix->row_elems, 128));
+    TRY(make_tmap_2d(&tq, ix->q_pack.p, nq_pad, ix->row_elems, 128));
     TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;
@@ -383,11 +396,13 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         }
         CU_TRY(cudaEventRecord(ix->ev0[slot], st));
     }
-    if (variant == 2) {
-        if (block_n == 64)
-            TRY((dispatch_ts2<64, 12, 4>(E, tx, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+    if (variant == 4) {
+        TRY((dispatch_ts2<64, 12, 0, 12, 4>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+    } else if (variant == 2) {
+        if (p.nkb <= 8)
+            TRY((dispatch_ts2<128, 8, 0, 4, 6>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
         else
-            TRY((dispatch_ts2<128, 8, 3>(E, tx, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+            TRY((dispatch_ts2<128, 8, 4, 4, 5>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
     } else if (variant == 3) {
         switch (E) {
             case 0: TRY(launch_gemm_topk_ss2<0>(tq, tx, p, grid, st)); break;

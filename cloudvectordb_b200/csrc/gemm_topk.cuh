@@ -385,44 +385,50 @@ constexpr size_t gemm_topk_ss_smem_bytes() {
 }
 
 // ===========================================================================
-// Flagship variant: CTA pair (cta_group::2), queries resident in TMEM.
+// CTA pair (cta_group::2, M = 256) with the QUERIES RESIDENT ON CHIP.
 //
 //   * a cluster of two CTAs (one SM pair) owns 256 queries; each CTA keeps its
-//     128 query rows in TENSOR MEMORY (bf16 pairs, 32 columns per 64-wide K
-//     block) for the whole work item, so the A operand is never re-read from
-//     shared memory or L2,
-//   * only database rows stream: per tile each CTA TMA-loads half of the
-//     BLOCK_N rows (all K blocks = one pipeline stage), the MMA
-//     (tcgen05.mma.cta_group::2, M = 256) reads both halves,
+//     128 query rows for the whole work item: the first KB_T 64-wide K blocks in
+//     TENSOR MEMORY (bf16 pairs, 32 columns per block, written with tcgen05.st)
+//     and, when K is larger, KB_S more blocks in shared memory ("tail", loaded
+//     once per item by TMA) -- the A operand is never re-streamed from L2,
+//   * only database rows stream: each CTA TMA-loads half of the BLOCK_N rows of
+//     a tile, KB_STAGE K blocks per pipeline stage; the MMA
+//     (tcgen05.mma.cta_group::2) reads both halves, with A from TMEM for the
+//     first KB_T blocks and from the shared-memory tail afterwards,
 //   * accumulators: two buffers of BLOCK_N fp32 columns after the A region
-//     (A 384 + 2 x 64 columns for K <= 768, A 256 + 2 x 128 for K <= 512),
+//     (KB_T*32 + 2*BLOCK_N == 512 TMEM columns),
 //   * the epilogue is the same threshold filter, one thread per query row.
 //
-// L2 -> SM traffic per SM is a third of the streaming (SS) kernel's and shared
-// memory is read at a third of its rate, which is what the power-capped B200
-// needs to hold its clocks.
+// Configurations: <128, 8, 0, 4, 6> for K <= 512, <128, 8, 4, 4, 5> for
+// K <= 768 (hybrid), <64, 12, 0, 12, 4> (all of K <= 768 in TMEM, N = 64).
+// L2 -> SM traffic per SM is a third of the streaming kernel's.
 // ===========================================================================
-template <int BLOCK_N, int KB_MAX, int STAGES, int E>
+template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES, int E>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ q_pack,
-                     const int q_row_elems, const GemmTopkParams p) {
-    constexpr int HALF_N = BLOCK_N / 2;                  // database rows this CTA loads per tile
-    constexpr uint32_t KB_BYTES = HALF_N * 128;          // one 64-wide K block of those rows
-    constexpr uint32_t STAGE_BYTES = KB_MAX * KB_BYTES;  // one tile, all K blocks
-    constexpr uint32_t A_COLS = KB_MAX * 32;             // TMEM columns holding the query tile
+gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
+                     const __nv_bfloat16* __restrict__ q_pack, const int q_row_elems, const GemmTopkParams p) {
+    constexpr int HALF_N = BLOCK_N / 2;                    // database rows this CTA loads per tile
+    constexpr uint32_t KB_BYTES = HALF_N * 128;            // one 64-wide K block of those rows
+    constexpr uint32_t STAGE_BYTES = KB_STAGE * KB_BYTES;  // one pipeline stage
+    constexpr uint32_t A_COLS = KB_T * 32;                 // TMEM columns holding the query tile
+    constexpr uint32_t TAIL_KB_BYTES = 128 * 128;          // one K block of this CTA's 128 query rows
+    constexpr uint32_t TAIL_BYTES = KB_S * TAIL_KB_BYTES;
     static_assert(A_COLS + 2 * BLOCK_N == 512, "TMEM budget: queries + two accumulators = 512 columns");
     constexpr int C = 32 * (E > 0 ? E : 1);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_b = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* smem_tail = smem;                     // [KB_S][128 rows][128 B], swizzled
+    uint8_t* smem_b = smem + TAIL_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TAIL_BYTES + STAGES * STAGE_BYTES);
     uint64_t* full_bar = bars;                     // leader CTA's copy is the live one
     uint64_t* empty_bar = bars + STAGES;           // per CTA
     uint64_t* tmem_full = bars + 2 * STAGES;       // per CTA
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // leader's copy
-    uint64_t* a_ready = bars + 2 * STAGES + 4;     // leader's copy
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    uint64_t* a_ready = bars + 2 * STAGES + 4;     // leader's copy: query rows are in TMEM (+ tail in smem)
+    uint64_t* a_free = bars + 2 * STAGES + 5;      // per CTA: all MMAs of the item have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -430,7 +436,10 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
     const int pair = blockIdx.x >> 1;
     const int n_pairs = gridDim.x >> 1;
 
-    if (warp == 0 && lane == 0) prefetch_tmap(&tmap_x);
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        if constexpr (KB_S > 0) prefetch_tmap(&tmap_q);
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -440,7 +449,8 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
         }
-        mbar_init(a_ready, 8);
+        mbar_init(a_ready, KB_S > 0 ? 9 : 8);  // + the leader producer's expect_tx for the tails
+        mbar_init(a_free, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -453,27 +463,46 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_items = p.q_tiles * p.n_slices;  // q_tiles counts 256-query tiles here
-    const int nkb = p.nkb;
+    const int nkb = p.nkb;                       // <= KB_T + KB_S
+    const int nkb_t = min(nkb, KB_T);            // K blocks served from TMEM
+    const int nkb_s = nkb - nkb_t;               // K blocks served from the smem tail
+    const int n_groups = (nkb + KB_STAGE - 1) / KB_STAGE;
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer (both CTAs, warp-uniform loop)
         int stage = 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, item_phase = 0;
         for (int w = pair; w < n_items; w += n_pairs) {
-            const int slice = w / p.q_tiles;
+            const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
             const int t0 = slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-            for (int t = t0; t < t1; ++t) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+            if constexpr (KB_S > 0) {
+                // the query tail of this item: wait until the previous item's MMAs are done with the old one
+                mbar_wait(a_free, item_phase ^ 1);
+                item_phase ^= 1;
                 if (elect_one_sync()) {
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * nkb * KB_BYTES);
-                    uint8_t* dst = smem_b + stage * STAGE_BYTES;
-                    const int row = t * BLOCK_N + static_cast<int>(rank) * HALF_N;
-                    for (int kb = 0; kb < nkb; ++kb)
-                        tma_load_2d_2sm(&tmap_x, &full_bar[stage], dst + kb * KB_BYTES, kb * 64, row, kEvictNormal);
+                    if (rank == 0) mbar_expect_tx(a_ready, 2u * nkb_s * TAIL_KB_BYTES);
+                    for (int kb = 0; kb < nkb_s; ++kb)
+                        tma_load_2d_2sm(&tmap_q, a_ready, smem_tail + kb * TAIL_KB_BYTES, (KB_T + kb) * 64,
+                                        qt * 256 + static_cast<int>(rank) * 128, kEvictLast);
                 }
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            for (int t = t0; t < t1; ++t) {
+                const int row = t * BLOCK_N + static_cast<int>(rank) * HALF_N;
+                for (int g = 0; g < n_groups; ++g) {
+                    const int kb0 = g * KB_STAGE, kb1 = min(kb0 + KB_STAGE, nkb);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one_sync()) {
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (kb1 - kb0) * KB_BYTES);
+                        uint8_t* dst = smem_b + stage * STAGE_BYTES;
+                        for (int kb = kb0; kb < kb1; ++kb)
+                            tma_load_2d_2sm(&tmap_x, &full_bar[stage], dst + (kb - kb0) * KB_BYTES, kb * 64, row,
+                                            kEvictNormal);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -488,27 +517,40 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
                 const int slice = w / p.q_tiles;
                 const int t0 = slice * p.tiles_per_slice;
                 const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-                mbar_wait(a_ready, item_phase);  // both CTAs have written their query rows to TMEM
+                mbar_wait(a_ready, item_phase);  // both CTAs hold their query rows (TMEM + tail)
                 item_phase ^= 1;
                 tc_fence_after();
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint32_t tmem_d = tmem_base + A_COLS + acc * BLOCK_N;
-                        const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b + stage * STAGE_BYTES));
-                        for (int kb = 0; kb < nkb; ++kb) {
-                            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((kb * KB_BYTES) >> 4);
+                    const uint32_t tmem_d = tmem_base + A_COLS + acc * BLOCK_N;
+                    for (int g = 0; g < n_groups; ++g) {
+                        const int kb0 = g * KB_STAGE, kb1 = min(kb0 + KB_STAGE, nkb);
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b + stage * STAGE_BYTES));
+                            for (int kb = kb0; kb < kb1; ++kb) {
+                                const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(((kb - kb0) * KB_BYTES) >> 4);
+                                if (KB_S == 0 || kb < KB_T) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_ts<2>(tmem_d, tmem_base + kb * 32 + kk * 8, b_desc + 2 * kk, idesc, (kb | kk) != 0);
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_ts<2>(tmem_d, tmem_base + kb * 32 + kk * 8, b_desc + 2 * kk, idesc,
+                                                   (kb | kk) != 0);
+                                } else {
+                                    const uint64_t a_desc =
+                                        make_smem_desc_sw128(smem_u32(smem_tail + (kb - KB_T) * TAIL_KB_BYTES));
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+                                }
+                            }
+                            umma_commit_2sm(&empty_bar[stage], 3);                        // frees the stage in both CTAs
+                            if (g == n_groups - 1) umma_commit_2sm(&tmem_full[acc], 3);   // accumulator ready in both CTAs
+                            if (KB_S > 0 && g == n_groups - 1 && t == t1 - 1) umma_commit_2sm(a_free, 3);
                         }
-                        umma_commit_2sm(&empty_bar[stage], 3);  // frees the stage in both CTAs
-                        umma_commit_2sm(&tmem_full[acc], 3);    // accumulator ready in both CTAs
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -536,8 +578,8 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
             // MMAs that read the old rows have retired.
             {
                 const uint4* src = reinterpret_cast<const uint4*>(q_pack + static_cast<size_t>(q_valid ? q_row : 0) * q_row_elems);
-                const int n_vec = q_valid ? (min(q_row_elems, nkb * 64) >> 3) : 0;  // 16-byte granules with data
-                for (int c16 = 0; c16 < nkb * 2; ++c16) {
+                const int n_vec = q_valid ? (min(q_row_elems, nkb_t * 64) >> 3) : 0;  // 16-byte granules with data
+                for (int c16 = 0; c16 < nkb_t * 2; ++c16) {
                     uint32_t r[16];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
@@ -774,9 +816,9 @@ constexpr size_t gemm_topk_ss2_smem_bytes() {
     return 1024 + size_t(STAGES) * (128 * 64 * 2 + (BLOCK_N / 2) * 64 * 2) + (2 * STAGES + 5) * 8 + 16;
 }
 
-template <int BLOCK_N, int KB_MAX, int STAGES>
+template <int BLOCK_N, int KB_S, int KB_STAGE, int STAGES>
 constexpr size_t gemm_topk_ts2_smem_bytes() {
-    return 1024 + size_t(STAGES) * KB_MAX * (BLOCK_N / 2) * 128 + (2 * STAGES + 6) * 8 + 16;
+    return 1024 + size_t(KB_S) * 128 * 128 + size_t(STAGES) * KB_STAGE * (BLOCK_N / 2) * 128 + (2 * STAGES + 7) * 8 + 16;
 }
 
 }  // namespace cvdb

@@ -65,7 +65,7 @@ typedef struct cvdb_search_opts {
     int64_t id_base;         /* added to every returned id (shard offset)                             */
     int profile;             /* 1: bracket the GEMM+top-k kernel with CUDA events (cvdb_index_last_kernel_ms) */
     int force_slices;        /* >0: override the database-slice heuristic (testing)                   */
-    int force_variant;       /* 0: auto; 1 / 2 / 3: force that kernel variant (cvdb_index_last_variant) */
+    int force_variant;       /* 0: auto; 1..4: force that kernel variant (cvdb_index_last_variant)   */
     int debug_flags;         /* kernel-tuning experiments only (results become invalid): 1 = skip the
                                 top-k scan, 2 = skip the TMEM read as well, 4 = no threshold sharing between slices */
 } cvdb_search_opts;
@@ -102,8 +102,9 @@ float cvdb_index_last_kernel_ms(cvdb_index_t idx);
 int cvdb_index_profile_ms(cvdb_index_t idx, float* out_ms, int max_n);
 /* algorithmic work of the last search: flops = 2*nq*ntotal*d*planes_factor, db bytes streamed once */
 int cvdb_index_last_work(cvdb_index_t idx, double* flops, double* db_bytes, int* n_slices, int* grid);
-/* kernel variant the last search used: 1 = single-CTA streaming kernel, 2 = CTA-pair kernel with
- * TMEM-resident queries, 3 = CTA-pair streaming kernel */
+/* kernel variant the last search used: 1 = single-CTA streaming kernel, 2 = CTA-pair kernel with the queries
+ * resident on chip (TMEM, plus a shared-memory tail for 512 < K <= 768; 128-column accumulators),
+ * 3 = CTA-pair streaming kernel, 4 = CTA-pair kernel with all of K <= 768 in TMEM (64-column accumulators) */
 int cvdb_index_last_variant(cvdb_index_t idx);
 
 /* -- shard/merge layer ----------------------------------------------------

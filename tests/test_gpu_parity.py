@@ -73,9 +73,10 @@ def test_bf16_kernel_matches_oracle_on_rounded_inputs(metric, n, d, nq, k):
     assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("metric,n,d,nq,k", [
-    ("ip", 5000, 768, 300, 10),    # K = 768: 64-column accumulators in the TMEM-resident variant
+    ("ip", 5000, 768, 300, 10),    # K = 768: TMEM + shared-memory tail (variant 2), all-TMEM N=64 (variant 4)
+    ("l2", 5000, 600, 300, 10),    # 10 K blocks: a partial tail
     ("l2", 7000, 384, 513, 1),     # K <= 512: 128-column accumulators, top-1 path
     ("ip", 3000, 100, 64, 50),
     ("l2", 300, 20, 5, 7),         # tiny: the peer CTA of a pair sees only out-of-bounds rows
