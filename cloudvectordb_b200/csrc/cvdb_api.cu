@@ -120,7 +120,7 @@ struct Index {
     __nv_bfloat16* x = nullptr;
     int num_sms = 0;
 
-    DevBuf gthr, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
+    DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
     bool has_groups = false;
 
     // ring of event pairs bracketing profiled GEMM+top-k launches (opts.profile)
@@ -382,6 +382,12 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     TRY(ix->gthr.ensure(static_cast<size_t>(nq) * 4));
     CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq) * 4, st));
     p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
+    {
+        const int64_t n_waves = ceil_div(n_items, std::min<int64_t>(workers, n_items));
+        TRY(ix->waves.ensure(static_cast<size_t>(n_waves) * 4));
+        CU_TRY(cudaMemsetAsync(ix->waves.p, 0, static_cast<size_t>(n_waves) * 4, st));
+        p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->waves.as<uint32_t>();
+    }
 
     CUtensorMap tq, tx;
     TRY(make_tmap_2d(&tq, ix->q_pack.p, nq_pad, ix->row_elems, 128));
@@ -515,7 +521,7 @@ int cvdb_index_destroy(cvdb_index_t h) {
     cvdb_guard g(ix->device);
     cudaDeviceSynchronize();
     if (ix->x) cudaFree(ix->x);
-    for (DevBuf* b : {&ix->gthr, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
+    for (DevBuf* b : {&ix->gthr, &ix->waves, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
                       &ix->ids_b, &ix->groups})
         b->release();
     for (int i = 0; i < Index::kProfSlots; ++i) {

@@ -51,8 +51,38 @@ struct GemmTopkParams {
     uint64_t* cand;  // [gridDim.x][128][32*E] candidate scratch (E>0)
     uint64_t* part;  // [nq][n_slices][k] per-slice results (keys)
     uint32_t* gthr;  // [nq] shared per-query threshold (ordered-float), zeroed before the launch
+    uint32_t* wave_cnt;  // [waves] producers that finished issuing the loads of their item in that wave (or null)
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
 };
+
+// ---------------------------------------------------------------------------
+// Soft wave alignment.  Work items are ordered slice-major so that CTAs running
+// at the same time stream the same database rows and share them through L2,
+// but with a static schedule CTAs drift apart over a launch (a 1 % speed
+// difference is more than the L2 can bridge) and every one ends up fetching
+// the database from HBM on its own.  Before starting the loads of its next
+// item a producer therefore waits until every producer has finished issuing
+// the loads of the current one.  It is only a performance hint: the wait gives
+// up after a bounded time, so it cannot deadlock even if some CTAs are not
+// resident.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void wave_arrive(uint32_t* cnt) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+}
+__device__ __forceinline__ void wave_wait(const uint32_t* cnt, uint32_t expected) {
+    const uint64_t t0 = globaltimer_ns();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= expected || globaltimer_ns() - t0 > 400000ull) break;
+        __nanosleep(256);
+    }
+}
+// producers (CTAs) that take part in wave `it`
+__device__ __forceinline__ uint32_t wave_members(int it, int n_items, int n_workers, int ctas_per_worker) {
+    const int left = n_items - it * n_workers;
+    return static_cast<uint32_t>((left < n_workers ? left : n_workers) * ctas_per_worker);
+}
 
 // ---------------------------------------------------------------------------
 // Per-thread (= per-query) selection state used by the epilogue warps.
@@ -269,10 +299,15 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // ------------------------------------------------------ TMA producer (warp-uniform loop)
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        int it = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
             const int t0 = slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            if (p.wave_cnt != nullptr && it > 0) {
+                if (elect_one_sync()) wave_wait(p.wave_cnt + it - 1, wave_members(it - 1, n_items, gridDim.x, 1));
+                __syncwarp();
+            }
             for (int t = t0; t < t1; ++t) {
                 for (int c = 0; c < p.n_combo; ++c) {
                     const int a_col = static_cast<int>((p.a_planes >> (4 * c)) & 0xF) * p.plane_cols;
@@ -291,6 +326,8 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     }
                 }
             }
+            if (p.wave_cnt != nullptr && elect_one_sync()) wave_arrive(p.wave_cnt + it);
+            __syncwarp();
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer (warp-uniform loop)
@@ -472,10 +509,15 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // ------------------------------------------------------ TMA producer (both CTAs, warp-uniform loop)
         int stage = 0;
         uint32_t phase = 0, item_phase = 0;
-        for (int w = pair; w < n_items; w += n_pairs) {
+        int it = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
             const int t0 = slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+            if (p.wave_cnt != nullptr && it > 0) {
+                if (elect_one_sync()) wave_wait(p.wave_cnt + it - 1, wave_members(it - 1, n_items, n_pairs, 2));
+                __syncwarp();
+            }
             if constexpr (KB_S > 0) {
                 // the query tail of this item: wait until the previous item's MMAs are done with the old one
                 mbar_wait(a_free, item_phase ^ 1);
@@ -504,6 +546,8 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.wave_cnt != nullptr && elect_one_sync()) wave_arrive(p.wave_cnt + it);
+            __syncwarp();
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer (leader only, warp-uniform loop)
@@ -698,11 +742,16 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = pair; w < n_items; w += n_pairs) {
+        int it = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
             const int t0 = slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             const int q_row0 = qt * 256 + static_cast<int>(rank) * 128;
+            if (p.wave_cnt != nullptr && it > 0) {
+                if (elect_one_sync()) wave_wait(p.wave_cnt + it - 1, wave_members(it - 1, n_items, n_pairs, 2));
+                __syncwarp();
+            }
             for (int t = t0; t < t1; ++t) {
                 const int x_row0 = t * BLOCK_N + static_cast<int>(rank) * HALF_N;
                 for (int c = 0; c < p.n_combo; ++c) {
@@ -722,6 +771,8 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     }
                 }
             }
+            if (p.wave_cnt != nullptr && elect_one_sync()) wave_arrive(p.wave_cnt + it);
+            __syncwarp();
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer (leader only)
