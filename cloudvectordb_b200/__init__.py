@@ -9,7 +9,8 @@ Everything numeric runs in hand-written sm_100a kernels behind the C ABI in
 """
 from .index import IndexFlat, IndexFlatIP, IndexFlatL2, merge_topk  # noqa: F401
 from .kmeans import Kmeans  # noqa: F401
-from .mining import mine_hard_negatives  # noqa: F401
+from .mining import mine_hard_negatives, mine_hard_negatives_sharded  # noqa: F401
 from .sharded import ShardedIndex  # noqa: F401
 
-__all__ = ["IndexFlat", "IndexFlatIP", "IndexFlatL2", "merge_topk", "Kmeans", "mine_hard_negatives", "ShardedIndex"]
+__all__ = ["IndexFlat", "IndexFlatIP", "IndexFlatL2", "merge_topk", "Kmeans", "mine_hard_negatives",
+           "mine_hard_negatives_sharded", "ShardedIndex"]

@@ -51,3 +51,45 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
     if _is_torch(outs_d[0]):
         return torch.cat(outs_d), torch.cat(outs_i)
     return np.concatenate(outs_d), np.concatenate(outs_i)
+
+
+def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, exclude_self: bool = True,
+                                chunk: int = 65536, max_chunks: Optional[int] = None):
+    """Self-join over a ShardedIndex (one process per GPU): every rank owns the rows
+    `local_emb` it added with add_local().  Anchor chunks are broadcast from their
+    owner, searched on every shard, merged (ShardedIndex.search) and kept by the owner.
+
+    Returns (D, I) for this rank's rows (global ids), like search().
+    `max_chunks` bounds the number of anchor chunks per owner (benchmarks)."""
+    import torch.distributed as dist
+    rank, world = index.rank, index.world
+    dev = local_emb.device
+    counts = index._counts
+    outs_d, outs_i = [], []
+    for owner in range(world):
+        n_owner = counts[owner]
+        base = sum(counts[:owner])
+        n_chunks = (n_owner + chunk - 1) // chunk
+        if max_chunks is not None:
+            n_chunks = min(n_chunks, max_chunks)
+        for c in range(n_chunks):
+            q0, q1 = c * chunk, min((c + 1) * chunk, n_owner)
+            if rank == owner:
+                q = local_emb[q0:q1].contiguous()
+                g = local_groups[q0:q1].to(torch.int32).contiguous() if local_groups is not None else None
+            else:
+                q = torch.empty((q1 - q0, local_emb.shape[1]), dtype=local_emb.dtype, device=dev)
+                g = torch.empty((q1 - q0,), dtype=torch.int32, device=dev) if local_groups is not None else None
+            if world > 1:
+                src = dist.get_global_rank(index.group, owner) if index.group is not None else owner
+                dist.broadcast(q, src=src, group=index.group)
+                if g is not None:
+                    dist.broadcast(g, src=src, group=index.group)
+            self_ids = torch.arange(base + q0, base + q1, device=dev) if exclude_self else None
+            D, I = index.search(q, k, self_ids=self_ids, group_q=g)
+            if rank == owner:
+                outs_d.append(D)
+                outs_i.append(I)
+    if not outs_d:
+        return (torch.empty((0, k), dtype=torch.float32, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
+    return torch.cat(outs_d), torch.cat(outs_i)

@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from cloudvectordb_b200 import IndexFlat, Kmeans, ShardedIndex  # noqa: E402
+from cloudvectordb_b200 import IndexFlat, Kmeans, ShardedIndex, mine_hard_negatives, mine_hard_negatives_sharded  # noqa: E402
 from cloudvectordb_b200.sharded import shard_bounds  # noqa: E402
 
 
@@ -44,6 +44,17 @@ def main():
         assert torch.equal(I2, I2_ref) and torch.equal(D2, D2_ref), f"{metric}: sharded exclusion != single GPU"
         Dh, Ih = sh.search(xq, k)                          # host queries -> host results
         assert not Dh.is_cuda and torch.equal(Ih, I_ref.cpu())
+    # sharded self-join == single-GPU self-join on the owner's rows
+    m, dm, km_ = 20_000, 64, 20
+    emb = torch.nn.functional.normalize(torch.randn((m, dm), generator=g), dim=1).bfloat16()
+    grp = (torch.arange(m) // 4).to(torch.int32)
+    D1, I1 = mine_hard_negatives(emb.to(dev), km_, grp.to(dev), device=local, chunk=4096)
+    shm = ShardedIndex(dm, "ip", "bf16", device=local)
+    lo, hi = shard_bounds(m, world, rank)
+    shm.add_local(emb[lo:hi].to(dev))
+    shm.set_groups_local(grp[lo:hi])
+    D2, I2 = mine_hard_negatives_sharded(shm, emb[lo:hi].to(dev), km_, grp[lo:hi].to(dev), chunk=3000)
+    assert torch.equal(I2, I1[lo:hi]) and torch.equal(D2, D1[lo:hi]), "sharded mining != single GPU"
     # k-means: sharded points, all-reduced update == single-rank update on all points
     pts = torch.nn.functional.normalize(torch.randn((40_000, 64), generator=g), dim=1).bfloat16()
     cent = pts[:128].float()
