@@ -55,11 +55,17 @@ class Kmeans:
         self._index.reset()
         self._index.add(c)
 
-    def step(self, x: torch.Tensor):
-        """One Lloyd iteration on this rank's points: returns (assign, objective)."""
+    def step(self, x: torch.Tensor, profile: bool = False):
+        """One Lloyd iteration on this rank's points: returns (assign, objective).
+        With profile=True, self.last_timing holds the device time (ms) of each phase."""
         lib = _C.lib()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if profile else None
+        if profile:
+            ev[0].record()
         self._set_centroids(self.centroids)
         assign, dist_sq = self._index.assign(x, return_dist=True)
+        if profile:
+            ev[1].record()
         sums = torch.zeros((self.k, self.d), dtype=torch.float32, device=x.device)
         counts = torch.zeros((self.k,), dtype=torch.int32, device=x.device)
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
@@ -67,12 +73,19 @@ class Kmeans:
         _C.check(lib.cvdb_kmeans_accumulate(x.data_ptr(), x.shape[0], self.d, dt, assign.data_ptr(), sums.data_ptr(),
                                             counts.data_ptr(), stream))
         obj = dist_sq.double().sum()
+        if profile:
+            ev[2].record()
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(sums, group=self.group)
             dist.all_reduce(counts, group=self.group)
             dist.all_reduce(obj, group=self.group)
         _C.check(lib.cvdb_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), self.k, self.d,
                                           self.centroids.data_ptr(), stream))
+        if profile:
+            ev[3].record()
+            torch.cuda.synchronize(self.device)
+            self.last_timing = {"assign_ms": ev[0].elapsed_time(ev[1]), "update_ms": ev[1].elapsed_time(ev[2]),
+                                "reduce_finalize_ms": ev[2].elapsed_time(ev[3])}
         self.last_counts = counts
         return assign, obj
 

@@ -77,7 +77,7 @@ def kmeans(f, peaks, n=12_500_000, d=384, K=65536):
     x = gen_rows(torch, DEV, 1234, 0, n, d, torch.bfloat16)
     km = Kmeans(d, K, niter=1, seed=42, storage="bf16", device=0)
     km.centroids = x[torch.randperm(n, device=DEV)[:K]].float().contiguous()
-    ms, (assign, obj) = timed(lambda: km.step(x), iters=2, warmup=1)
+    ms, (assign, obj) = timed(lambda: km.step(x, profile=True), iters=2, warmup=1)
     flops = 2.0 * n * K * d
     tf = flops / ms / 1e9
     # assignment agreement with a torch fp32 reference on a subsample
@@ -96,7 +96,7 @@ def kmeans(f, peaks, n=12_500_000, d=384, K=65536):
         gap_ok = bool(gap < 1e-3)
     emit(f, config="kmeans_iter", points_local=n, d=d, K=K, ms_per_iter=ms, iters_per_s=1e3 / ms, tflops_whole_iter=tf,
          frac_sustained=tf / peaks["bf16_tflops_sustained"], frac_burst=tf / peaks["bf16_tflops"],
-         assign_agreement_subsample=agree, disagreements_are_near_ties=gap_ok,
+         phases_ms=km.last_timing, assign_agreement_subsample=agree, disagreements_are_near_ties=gap_ok,
          nonempty_clusters=int((km.last_counts > 0).sum()))
     del x
 

@@ -97,14 +97,14 @@ def main():
         km.centroids = c0.clone()
         objs, times = [], []
         for _ in range(a.iters):
-            ms, (_, obj) = sync_time(lambda: km.step(x))
+            ms, (_, obj) = sync_time(lambda: km.step(x, profile=True))
             times.append(ms)
             objs.append(float(obj))
         flops = 2.0 * n * world * K * d
         ms = float(np.median(times))
         emit(config="kmeans_sharded", world=world, points_total=n * world, d=d, K=K, ms_per_iter=ms, iters_per_s=1e3 / ms,
              tflops_aggregate=flops / ms / 1e9, frac_sustained_per_gpu=flops / ms / 1e9 / world / peaks["bf16_tflops_sustained"],
-             objective=objs, objective_non_increasing=all(b <= a_ * (1 + 1e-6) for a_, b in zip(objs, objs[1:])))
+             rank0_phases_ms=km.last_timing, objective=objs, objective_non_increasing=all(b <= a_ * (1 + 1e-6) for a_, b in zip(objs, objs[1:])))
         del x, km
         torch.cuda.empty_cache()
     if "small" in which:

@@ -202,7 +202,11 @@ def main():
                   ("perf_1M_l2", (1_000_000, 765, 10000, 10), dict(metric="l2")),
                   ("perf_1M_d384_k1", (1_000_000, 384, 100000, 1), dict(metric="l2")),
                   ("perf_1M_d512", (1_000_000, 512, 10000, 10), {}),
-                  ("perf_small_batch", (4_000_000, 768, 64, 10), {})]
+                  ("perf_small_batch", (4_000_000, 768, 64, 10), {}),
+                  ("perf_small_256", (4_000_000, 768, 256, 10), {}),
+                  ("perf_small_200", (4_000_000, 768, 200, 10), {}),
+                  ("perf_mid_1024", (4_000_000, 768, 1024, 10), {}),
+                  ("perf_mid_512", (4_000_000, 768, 512, 10), {})]
             if a.big:
                 pc.append(("perf_10M", (10_000_000, 768, 10000, 10), {}))
             for nm, args, kw in pc:
