@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="database rows of the bounded CPU sample")
     ap.add_argument("--cpu-nq", type=int, default=2048, help="queries of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dbg", type=int, default=0, help="kernel debug flags (tuning experiments)")
     ap.add_argument("--slices", type=int, default=0, help="override the database-slice heuristic")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 streaming kernel, 2 CTA-pair/TMEM kernel")
     return ap.parse_args()
@@ -212,6 +213,8 @@ def run_ours(a):
     vkw = {"force_variant": a.variant} if (a.variant and world == 1) else {}
     if a.slices and world == 1:
         vkw["force_slices"] = a.slices
+    if a.dbg and world == 1:
+        vkw["debug_flags"] = a.dbg
 
     def barrier():
         if world > 1:

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvdb_b200.so")
+LIB_PATH = os.environ.get("CVDB_LIB_PATH") or os.path.join(_HERE, "libcvdb_b200.so")  # env override: A/B of builds
 
 OK, EINVAL, ECUDA, ENOMEM, ELIMIT = 0, -1, -2, -3, -4
 METRIC_IP, METRIC_L2 = 0, 1

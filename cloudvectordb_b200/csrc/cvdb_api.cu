@@ -325,6 +325,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.k = k;
     p.dbg = opts ? opts->debug_flags : 0;
     p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
+    p.k16 = (opts && (opts->debug_flags & 16)) ? 4 * p.nkb : static_cast<int>(ceil_div(ix->Kp, 16));
     p.plane_cols = ix->Kp;
     if (ix->planes == 1) {
         p.n_combo = 1;
@@ -342,16 +343,16 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     //       first 512 of K, shared-memory tail beyond; 128-column accumulators): large batches,
     //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage),
     //   4 = CTA pair with all of K <= 768 in TMEM and 64-column accumulators (comparison only).
-    const bool ts2_ok = ix->planes == 1 && p.nkb <= 12;
+    const bool ts2_ok = ix->planes == 1 && p.nkb <= 13;  // padded K <= 832 (768 + the L2 norm columns)
     int variant = (ts2_ok && nq > 256) ? 2 : 1;
     if (opts && opts->force_variant == 1) variant = 1;
     if (opts && opts->force_variant == 3) variant = 3;
     if (opts && opts->force_variant == 2) {
-        if (!ts2_ok) return fail(CVDB_EINVAL, "variant 2 needs bf16 storage and padded d <= 768");
+        if (!ts2_ok) return fail(CVDB_EINVAL, "variant 2 needs bf16 storage and padded d <= 832");
         variant = 2;
     }
     if (opts && opts->force_variant == 4) {
-        if (!ts2_ok) return fail(CVDB_EINVAL, "variant 4 needs bf16 storage and padded d <= 768");
+        if (!(ts2_ok && p.nkb <= 12)) return fail(CVDB_EINVAL, "variant 4 needs bf16 storage and padded d <= 768");
         variant = 4;
     }
     const bool resident = variant == 2 || variant == 4;
@@ -407,8 +408,10 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     } else if (variant == 2) {
         if (p.nkb <= 8)
             TRY((dispatch_ts2<128, 8, 0, 4, 6>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
-        else
+        else if (p.nkb <= 12)
             TRY((dispatch_ts2<128, 8, 4, 4, 5>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+        else  // 13 K blocks: d = 768 with the three L2 norm columns
+            TRY((dispatch_ts2<128, 8, 5, 5, 3>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
     } else if (variant == 3) {
         switch (E) {
             case 0: TRY(launch_gemm_topk_ss2<0>(tq, tx, p, grid, st)); break;

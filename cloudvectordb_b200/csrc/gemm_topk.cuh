@@ -41,6 +41,7 @@ struct GemmTopkParams {
     int n_slices;         // database slices
     int tiles_per_slice;  // in BLOCK_N units
     int nkb;              // 64-element K blocks per plane
+    int k16;              // 16-element MMA K steps per plane (ceil(Kp / 16)): the last K block may need fewer than 4
     int n_combo;          // (A plane, B plane) pairs accumulated per tile: 1 (bf16) or 6 (exact split)
     int plane_cols;       // columns per plane (Kp)
     uint32_t a_planes;    // 4 bits per combo: plane of the A (query) operand
@@ -350,10 +351,12 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     if (elect_one_sync()) {
                         const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
                         const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+                        const int kb = s % p.nkb;
+                        const int nk = min(4, p.k16 - 4 * kb);  // the last K block of a plane may be partly padding
 #pragma unroll
                         for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
                             // +32 bytes along K inside the 128-byte swizzled row
-                            umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                            if (kk < nk) umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
                         }
                         umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                         if (s == ksteps - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -575,17 +578,30 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                             const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b + stage * STAGE_BYTES));
                             for (int kb = kb0; kb < kb1; ++kb) {
                                 const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(((kb - kb0) * KB_BYTES) >> 4);
+                                // the last K block may be partly padding: issue only the K=16 steps that hold data
+                                const int nk = (kb == nkb - 1) ? p.k16 - 4 * kb : 4;
                                 if (KB_S == 0 || kb < KB_T) {
+                                    if (nk == 4) {
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        umma_ts<2>(tmem_d, tmem_base + kb * 32 + kk * 8, b_desc + 2 * kk, idesc,
-                                                   (kb | kk) != 0);
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            umma_ts<2>(tmem_d, tmem_base + kb * 32 + kk * 8, b_desc + 2 * kk, idesc,
+                                                       (kb | kk) != 0);
+                                    } else {
+                                        for (int kk = 0; kk < nk; ++kk)
+                                            umma_ts<2>(tmem_d, tmem_base + kb * 32 + kk * 8, b_desc + 2 * kk, idesc,
+                                                       (kb | kk) != 0);
+                                    }
                                 } else {
                                     const uint64_t a_desc =
                                         make_smem_desc_sw128(smem_u32(smem_tail + (kb - KB_T) * TAIL_KB_BYTES));
+                                    if (nk == 4) {
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+                                    } else {
+                                        for (int kk = 0; kk < nk; ++kk)
+                                            umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+                                    }
                                 }
                             }
                             umma_commit_2sm(&empty_bar[stage], 3);                        // frees the stage in both CTAs
@@ -796,9 +812,10 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         if (elect_one_sync()) {
                             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
                             const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+                            const int nk = min(4, p.k16 - 4 * (s % p.nkb));
 #pragma unroll
                             for (int kk = 0; kk < BLOCK_K / 16; ++kk)
-                                umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                                if (kk < nk) umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
                             umma_commit_2sm(&empty_bar[stage], 3);
                             if (s == ksteps - 1) umma_commit_2sm(&tmem_full[acc], 3);
                         }

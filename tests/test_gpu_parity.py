@@ -94,6 +94,23 @@ def test_every_kernel_variant_matches_oracle(variant, metric, n, d, nq, k):
     assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("d", [768, 770, 829])
+def test_l2_with_13_k_blocks(variant, d):
+    """d = 768 plus the three L2 norm columns needs a 13th K block (one MMA K-step of it)."""
+    rng = np.random.default_rng(d)
+    n, nq, k = 6000, 400, 10
+    xb, xq = O.bf16_round(unit_rows(rng, n, d)), O.bf16_round(unit_rows(rng, nq, d))
+    D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_L2)
+    idx = make_index(d, "l2", "bf16")
+    idx.add(xb)
+    D, I = idx.search(xq, k, force_variant=variant)
+    if variant:
+        assert idx.last_work()["variant"] == variant
+    idx.close()
+    assert_parity(D, I, D_ref, I_ref, "l2", tie_tol=2e-5)
+
+
 @pytest.mark.parametrize("variant", [1, 3])
 def test_exact_storage_on_both_streaming_variants(variant):
     rng = np.random.default_rng(77)
