@@ -8,9 +8,10 @@ Everything numeric runs in hand-written sm_100a kernels behind the C ABI in
 ``include/cvdb_b200.h``; this package only moves pointers.
 """
 from .index import IndexFlat, IndexFlatIP, IndexFlatL2, merge_topk  # noqa: F401
+from .ivf import IndexIVFFlat  # noqa: F401
 from .kmeans import Kmeans  # noqa: F401
 from .mining import mine_hard_negatives, mine_hard_negatives_sharded  # noqa: F401
 from .sharded import ShardedIndex  # noqa: F401
 
-__all__ = ["IndexFlat", "IndexFlatIP", "IndexFlatL2", "merge_topk", "Kmeans", "mine_hard_negatives",
+__all__ = ["IndexIVFFlat", "IndexFlat", "IndexFlatIP", "IndexFlatL2", "merge_topk", "Kmeans", "mine_hard_negatives",
            "mine_hard_negatives_sharded", "ShardedIndex"]

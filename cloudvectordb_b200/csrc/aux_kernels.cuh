@@ -221,6 +221,109 @@ __global__ void kmeans_finalize_kernel(const float* __restrict__ sums, const int
     if (c > 0) centroids[i] = sums[i] / static_cast<float>(c);
 }
 
+// ---------------------------------------------------------------------------
+// Inverted-list (IVF) plumbing.
+// ---------------------------------------------------------------------------
+// out[p] = in[perm[p]] for whole packed rows (row_bytes is a multiple of 16)
+__global__ void permute_rows_kernel(const uint4* __restrict__ in, const int32_t* __restrict__ perm, int64_t n,
+                                    int row_vec16, uint4* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const uint4* src = in + static_cast<int64_t>(perm[r]) * row_vec16;
+        uint4* dst = out + r * row_vec16;
+        for (int c = lane; c < row_vec16; c += 32) dst[c] = src[c];
+    }
+}
+
+// (query, probe) pairs per list; pairs naming an invalid or empty list are dropped
+__global__ void ivf_count_pairs_kernel(const int32_t* __restrict__ probes, int64_t n_pairs, int nlist,
+                                       const int32_t* __restrict__ list_off, int32_t* __restrict__ cnt) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int l = probes[i];
+    if (l < 0 || l >= nlist || list_off[l + 1] == list_off[l]) return;
+    atomicAdd(cnt + l, 1);
+}
+
+// single block: exclusive scans over the lists -> pair_off[l] (first gathered row of list l),
+// item_off[l] (first work item of list l); scal[0] = total items, scal[1] = total gathered rows
+__global__ void ivf_scan_lists_kernel(const int32_t* __restrict__ cnt, int nlist, int32_t* __restrict__ pair_off,
+                                      int32_t* __restrict__ item_off, int32_t* __restrict__ scal) {
+    __shared__ int s_pairs[1024], s_items[1024];
+    __shared__ int base_pairs, base_items;
+    const int tid = threadIdx.x;
+    if (tid == 0) { base_pairs = 0; base_items = 0; }
+    __syncthreads();
+    for (int l0 = 0; l0 < nlist; l0 += 1024) {
+        const int l = l0 + tid;
+        const int c = l < nlist ? cnt[l] : 0;
+        const int it = (c + 127) >> 7;
+        s_pairs[tid] = c;
+        s_items[tid] = it;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+            const int a = tid >= o ? s_pairs[tid - o] : 0, b = tid >= o ? s_items[tid - o] : 0;
+            __syncthreads();
+            s_pairs[tid] += a;
+            s_items[tid] += b;
+            __syncthreads();
+        }
+        if (l < nlist) {
+            pair_off[l] = base_pairs + s_pairs[tid] - c;
+            item_off[l] = base_items + s_items[tid] - it;
+        }
+        __syncthreads();
+        if (tid == 1023) { base_pairs += s_pairs[1023]; base_items += s_items[1023]; }
+        __syncthreads();
+    }
+    if (tid == 0) { scal[0] = base_items; scal[1] = base_pairs; }
+}
+
+// work items of every probed list: up to 128 gathered query rows x the rows of the list
+struct IvfItem { int a_row0, a_rows, x_row0, x_rows; };
+__global__ void ivf_make_items_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ pair_off,
+                                      const int32_t* __restrict__ item_off, const int32_t* __restrict__ list_off,
+                                      int nlist, IvfItem* __restrict__ items) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlist) return;
+    const int c = cnt[l];
+    for (int i = 0; i * 128 < c; ++i) {
+        IvfItem it;
+        it.a_row0 = pair_off[l] + i * 128;
+        it.a_rows = min(128, c - i * 128);
+        it.x_row0 = list_off[l];
+        it.x_rows = list_off[l + 1] - list_off[l];
+        items[item_off[l] + i] = it;
+    }
+}
+
+// one warp per pair: claim a slot next to the other pairs of the same list, record where the
+// pair's result goes, and copy the packed query row there
+__global__ void ivf_scatter_pairs_kernel(const int32_t* __restrict__ probes, int64_t n_pairs, int nprobe, int nlist,
+                                         const int32_t* __restrict__ list_off, const int32_t* __restrict__ pair_off,
+                                         int32_t* __restrict__ cursor, const uint4* __restrict__ q_pack, int row_vec16,
+                                         int32_t* __restrict__ pair_query, int32_t* __restrict__ pair_dst,
+                                         uint4* __restrict__ qg) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_pairs) return;
+    const int l = probes[i];
+    if (l < 0 || l >= nlist || list_off[l + 1] == list_off[l]) return;
+    int pos = 0;
+    if (lane == 0) pos = pair_off[l] + atomicAdd(cursor + l, 1);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    const int q = static_cast<int>(i / nprobe);
+    if (lane == 0) {
+        pair_query[pos] = q;
+        pair_dst[pos] = static_cast<int32_t>(i);
+    }
+    const uint4* src = q_pack + static_cast<int64_t>(q) * row_vec16;
+    uint4* dst = qg + static_cast<int64_t>(pos) * row_vec16;
+    for (int c = lane; c < row_vec16; c += 32) dst[c] = src[c];
+}
+
 // Exact-mode rescoring: recompute the score of each returned row from the
 // three bf16 planes (their sum reproduces the fp32 value) with fp32 FMAs, so
 // the reported distance does not carry tensor-core accumulation order effects.

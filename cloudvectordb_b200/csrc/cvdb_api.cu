@@ -120,6 +120,11 @@ struct Index {
     __nv_bfloat16* x = nullptr;
     int num_sms = 0;
 
+    // inverted-list (IVF) layout: rows stored list-major after cvdb_index_group_rows
+    bool grouped = false;
+    int nlist = 0;
+    DevBuf row_ids, list_off, ivf_cnt, ivf_pair_off, ivf_item_off, ivf_cursor, ivf_scal, ivf_items, ivf_pair_query,
+        ivf_pair_dst, ivf_qg, ivf_probes;
     DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
     bool has_groups = false;
 
@@ -466,6 +471,116 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     return CVDB_OK;
 }
 
+static_assert(sizeof(IvfItem) == sizeof(GroupItem), "item layouts must agree");
+constexpr int kGroupedBlockN = 128;
+constexpr int kGroupedStages = 6;
+
+template <int E>
+int launch_grouped(const CUtensorMap& tq, const CUtensorMap& tx, const GroupedParams& p, int grid, cudaStream_t st) {
+    auto kern = gemm_topk_grouped_kernel<kGroupedBlockN, kGroupedStages, E>;
+    constexpr size_t smem = gemm_topk_ss_smem_bytes<kGroupedBlockN, kGroupedStages>();
+    static bool configured = false;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    kern<<<grid, 256, smem, st>>>(tq, tx, p);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+// Search `nq` queries, each restricted to the `nprobe` inverted lists named in probes[nq][nprobe]
+// (device pointers; D/I device outputs).
+int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, const int32_t* probes, int nprobe,
+                        float* D, int64_t* I, cudaStream_t st) {
+    const int E = pick_E(k);
+    const int C = 32 * (E ? E : 1);
+    const int l2 = ix->metric == CVDB_METRIC_L2;
+    const int64_t n_pairs = nq * nprobe;
+    const int nlist = ix->nlist;
+    const int row_vec16 = ix->row_elems * 2 / 16;
+
+    TRY(ix->q_pack.ensure(static_cast<size_t>(nq) * ix->row_elems * 2));
+    TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
+    TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, ix->q_norm.as<float>(), st));
+
+    // --- group the (query, probe) pairs by list
+    const int64_t max_items = std::min<int64_t>(nlist, n_pairs) + n_pairs / 128 + 1;
+    const int64_t pairs_pad = n_pairs + 128;  // the last item's A box may run past the last gathered row
+    TRY(ix->ivf_cnt.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_cursor.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_pair_off.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_item_off.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_scal.ensure(16));
+    TRY(ix->ivf_items.ensure(static_cast<size_t>(max_items) * sizeof(IvfItem)));
+    TRY(ix->ivf_pair_query.ensure(static_cast<size_t>(pairs_pad) * 4));
+    TRY(ix->ivf_pair_dst.ensure(static_cast<size_t>(pairs_pad) * 4));
+    TRY(ix->ivf_qg.ensure(static_cast<size_t>(pairs_pad) * ix->row_elems * 2));
+    CU_TRY(cudaMemsetAsync(ix->ivf_cnt.p, 0, static_cast<size_t>(nlist) * 4, st));
+    CU_TRY(cudaMemsetAsync(ix->ivf_cursor.p, 0, static_cast<size_t>(nlist) * 4, st));
+    const int32_t* list_off = ix->list_off.as<int32_t>();
+    ivf_count_pairs_kernel<<<static_cast<unsigned>(ceil_div(n_pairs, 256)), 256, 0, st>>>(probes, n_pairs, nlist, list_off,
+                                                                                          ix->ivf_cnt.as<int32_t>());
+    ivf_scan_lists_kernel<<<1, 1024, 0, st>>>(ix->ivf_cnt.as<int32_t>(), nlist, ix->ivf_pair_off.as<int32_t>(),
+                                               ix->ivf_item_off.as<int32_t>(), ix->ivf_scal.as<int32_t>());
+    ivf_make_items_kernel<<<static_cast<unsigned>(ceil_div(nlist, 256)), 256, 0, st>>>(
+        ix->ivf_cnt.as<int32_t>(), ix->ivf_pair_off.as<int32_t>(), ix->ivf_item_off.as<int32_t>(), list_off, nlist,
+        ix->ivf_items.as<IvfItem>());
+    ivf_scatter_pairs_kernel<<<static_cast<unsigned>(ceil_div(n_pairs, 8)), 256, 0, st>>>(
+        probes, n_pairs, nprobe, nlist, list_off, ix->ivf_pair_off.as<int32_t>(), ix->ivf_cursor.as<int32_t>(),
+        ix->q_pack.as<uint4>(), row_vec16, ix->ivf_pair_query.as<int32_t>(), ix->ivf_pair_dst.as<int32_t>(),
+        ix->ivf_qg.as<uint4>());
+    g_launches += 4;
+    CU_TRY(cudaGetLastError());
+    int32_t scal[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(scal, ix->ivf_scal.p, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));  // the item count sizes the grid
+    const int n_items = scal[0];
+
+    TRY(ix->part.ensure(static_cast<size_t>(std::max<int64_t>(n_pairs, 1)) * k * 8));
+    CU_TRY(cudaMemsetAsync(ix->part.p, 0, static_cast<size_t>(n_pairs) * k * 8, st));  // dropped pairs stay empty
+    TRY(ix->gthr.ensure(static_cast<size_t>(nq) * 4));
+    CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq) * 4, st));
+    if (n_items > 0) {
+        const int grid = std::min(ix->num_sms, n_items);
+        if (E > 0) TRY(ix->cand.ensure(static_cast<size_t>(grid) * 128 * C * 8));
+        GroupedParams p{};
+        p.n_items = n_items;
+        p.k = k;
+        p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
+        p.k16 = static_cast<int>(ceil_div(ix->Kp, 16));
+        p.items = reinterpret_cast<const GroupItem*>(ix->ivf_items.p);
+        p.pair_query = ix->ivf_pair_query.as<int32_t>();
+        p.pair_dst = ix->ivf_pair_dst.as<int32_t>();
+        p.row_ids = ix->row_ids.as<int32_t>();
+        p.cand = ix->cand.as<uint64_t>();
+        p.part = ix->part.as<uint64_t>();
+        p.gthr = ix->gthr.as<uint32_t>();
+        CUtensorMap tq, tx;
+        TRY(make_tmap_2d(&tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 128));
+        TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, kGroupedBlockN));
+        switch (E) {
+            case 0: TRY(launch_grouped<0>(tq, tx, p, grid, st)); break;
+            case 1: TRY(launch_grouped<1>(tq, tx, p, grid, st)); break;
+            case 2: TRY(launch_grouped<2>(tq, tx, p, grid, st)); break;
+            case 4: TRY(launch_grouped<4>(tq, tx, p, grid, st)); break;
+            case 8: TRY(launch_grouped<8>(tq, tx, p, grid, st)); break;
+            default: TRY(launch_grouped<16>(tq, tx, p, grid, st)); break;
+        }
+    }
+    ix->last_flops = 0;
+    ix->last_slices = nprobe;
+    ix->last_grid = n_items;
+    ix->last_variant = 5;
+    const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
+    merge_partials_kernel<int64_t><<<blocks, 256, 0, st>>>(ix->part.as<uint64_t>(), nq, nprobe * k, k, l2,
+                                                           ix->q_norm.as<float>(), 0, D, I);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
 int check_index(cvdb_index_t h) {
     if (!h) return fail(CVDB_EINVAL, "null index handle");
     return CVDB_OK;
@@ -524,6 +639,9 @@ int cvdb_index_destroy(cvdb_index_t h) {
     cvdb_guard g(ix->device);
     cudaDeviceSynchronize();
     if (ix->x) cudaFree(ix->x);
+    for (DevBuf* b : {&ix->row_ids, &ix->list_off, &ix->ivf_cnt, &ix->ivf_pair_off, &ix->ivf_item_off, &ix->ivf_cursor,
+                      &ix->ivf_scal, &ix->ivf_items, &ix->ivf_pair_query, &ix->ivf_pair_dst, &ix->ivf_qg, &ix->ivf_probes})
+        b->release();
     for (DevBuf* b : {&ix->gthr, &ix->waves, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
                       &ix->ids_b, &ix->groups})
         b->release();
@@ -540,6 +658,7 @@ int cvdb_index_reset(cvdb_index_t h) {
     Index* ix = reinterpret_cast<Index*>(h);
     ix->ntotal = 0;
     ix->has_groups = false;
+    ix->grouped = false;
     return CVDB_OK;
 }
 
@@ -583,6 +702,7 @@ int cvdb_index_add(cvdb_index_t h, const void* x, int64_t n, int dtype, int on_d
     }
     ix->ntotal += n;
     ix->has_groups = false;
+    ix->grouped = false;  // new rows are not in any list yet
     return CVDB_OK;
 }
 
@@ -614,6 +734,8 @@ int cvdb_index_search(cvdb_index_t h, const void* q, int64_t nq, int dtype, int 
     if (!q || !D || !I) return fail(CVDB_EINVAL, "q, D and I must be non-null");
     if (opts && opts->group_q && !ix->has_groups)
         return fail(CVDB_EINVAL, "group_q given but the index has no groups (cvdb_index_set_groups)");
+    if (ix->grouped)
+        return fail(CVDB_EINVAL, "rows are stored list-major (cvdb_index_group_rows): use cvdb_index_search_lists");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
@@ -731,6 +853,83 @@ int cvdb_index_last_work(cvdb_index_t h, double* flops, double* db_bytes, int* n
 }
 
 int cvdb_index_last_variant(cvdb_index_t h) { return h ? reinterpret_cast<Index*>(h)->last_variant : -1; }
+
+int cvdb_index_group_rows(cvdb_index_t h, const int32_t* perm, const int32_t* row_ids, const int32_t* list_offsets,
+                          int nlist, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->planes != 1) return fail(CVDB_EINVAL, "inverted lists need bf16 storage");
+    if (nlist < 1) return fail(CVDB_EINVAL, "nlist < 1");
+    if (!perm || !row_ids || !list_offsets) return fail(CVDB_EINVAL, "null pointer");
+    if (ix->ntotal == 0) return fail(CVDB_EINVAL, "empty index");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = static_cast<size_t>(ix->ntotal) * ix->row_elems * 2;
+    __nv_bfloat16* nx = nullptr;
+    cudaError_t e = cudaMalloc(&nx, bytes);
+    if (e != cudaSuccess) return fail(CVDB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    const int64_t blocks = std::min<int64_t>(ceil_div(ix->ntotal, 8), 148 * 32);
+    permute_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(ix->x), perm,
+                                                                         ix->ntotal, ix->row_elems * 2 / 16,
+                                                                         reinterpret_cast<uint4*>(nx));
+    ++g_launches;
+    TRY(ix->row_ids.ensure(static_cast<size_t>(ix->ntotal) * 4));
+    TRY(ix->list_off.ensure(static_cast<size_t>(nlist + 1) * 4));
+    CU_TRY(cudaMemcpyAsync(ix->row_ids.p, row_ids, static_cast<size_t>(ix->ntotal) * 4, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ix->list_off.p, list_offsets, static_cast<size_t>(nlist + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(ix->x);
+    ix->x = nx;
+    ix->capacity = ix->ntotal;
+    ix->grouped = true;
+    ix->nlist = nlist;
+    ix->has_groups = false;
+    return CVDB_OK;
+}
+
+int cvdb_index_search_lists(cvdb_index_t h, const void* q, int64_t nq, int dtype, int k, const int32_t* probes, int nprobe,
+                            float* D, int64_t* I, int on_device, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix->grouped) return fail(CVDB_EINVAL, "rows are not grouped into lists (cvdb_index_group_rows)");
+    if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
+    if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
+    if (nprobe < 1 || nprobe > 4096) return fail(CVDB_ELIMIT, "nprobe=%d outside [1, 4096]", nprobe);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (nq == 0) return CVDB_OK;
+    if (!q || !probes || !D || !I) return fail(CVDB_EINVAL, "q, probes, D and I must be non-null");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    // bound the gathered-query scratch: at most 2^18 (query, probe) pairs per launch
+    const int64_t chunk = std::max<int64_t>(1, (int64_t(1) << 18) / nprobe);
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t m = std::min(chunk, nq - q0);
+        const void* qsrc = static_cast<const char*>(q) + q0 * ix->d * esz;
+        const int32_t* psrc = probes + q0 * nprobe;
+        float* Dd = D + q0 * k;
+        int64_t* Id = I + q0 * k;
+        if (!on_device) {
+            TRY(ix->stage_in.ensure(static_cast<size_t>(m) * ix->d * esz));
+            CU_TRY(cudaMemcpyAsync(ix->stage_in.p, qsrc, static_cast<size_t>(m) * ix->d * esz, cudaMemcpyHostToDevice, st));
+            qsrc = ix->stage_in.p;
+            TRY(ix->ivf_probes.ensure(static_cast<size_t>(m) * nprobe * 4));
+            CU_TRY(cudaMemcpyAsync(ix->ivf_probes.p, psrc, static_cast<size_t>(m) * nprobe * 4, cudaMemcpyHostToDevice, st));
+            psrc = ix->ivf_probes.as<int32_t>();
+            TRY(ix->out_d.ensure(static_cast<size_t>(m) * k * 4));
+            TRY(ix->out_i.ensure(static_cast<size_t>(m) * k * 8));
+            Dd = ix->out_d.as<float>();
+            Id = ix->out_i.as<int64_t>();
+        }
+        TRY(search_lists_device(ix, qsrc, m, dtype, k, psrc, nprobe, Dd, Id, st));
+        if (!on_device) {
+            CU_TRY(cudaMemcpyAsync(D + q0 * k, Dd, static_cast<size_t>(m) * k * 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(I + q0 * k, Id, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    return CVDB_OK;
+}
 
 int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric, float* D,
                     int64_t* I, int on_device, void* stream) {

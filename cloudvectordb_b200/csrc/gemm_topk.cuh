@@ -425,6 +425,255 @@ constexpr size_t gemm_topk_ss_smem_bytes() {
 }
 
 // ===========================================================================
+// Grouped variant for inverted-list (IVF) search.  The database rows are stored
+// list-major; a work item is (one inverted list, up to 128 of the (query, probe)
+// pairs that probe it).  The pairs' query rows have been gathered next to each
+// other (qg), so the A tile is a plain TMA box again; B tiles walk the rows of
+// the list.  Same pipeline and epilogue as the single-CTA streaming kernel; the
+// differences are the item table, per-lane destinations (pair -> part[query][probe])
+// and candidate ids translated to the caller's row ids (row_ids) when a
+// candidate is appended.  Thresholds are shared per QUERY across its probes.
+// ===========================================================================
+struct GroupItem {
+    int a_row0;  // first gathered query row of the item
+    int a_rows;  // valid gathered rows (<= 128)
+    int x_row0;  // first database row of the list (list-major storage)
+    int x_rows;  // rows in the list
+};
+
+struct GroupedParams {
+    int n_items;
+    int k;
+    int nkb, k16;
+    const GroupItem* items;
+    const int32_t* pair_query;  // [pairs] query id of each gathered row
+    const int32_t* pair_dst;    // [pairs] output slot (query * nprobe + probe) of each gathered row
+    const int32_t* row_ids;     // [n_rows] caller-visible id of each stored row (or null: position)
+    uint64_t* cand;             // [gridDim.x][128][32*E]
+    uint64_t* part;             // [nq * nprobe][k]
+    uint32_t* gthr;             // [nq]
+};
+
+template <int E>
+__device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0,
+                                                   uint32_t row_end, const int32_t* __restrict__ row_ids, int k) {
+    float m8[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float m = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 3])), __uint_as_float(v[8 * g + 4]));
+        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 5])), __uint_as_float(v[8 * g + 6]));
+        m8[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+    }
+    const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    if (!__any_sync(0xffffffffu, m > st.thr)) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
+        if constexpr (E > 0) make_room<E>(st, k);
+#pragma unroll
+        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+            const float s = __uint_as_float(v[j]);
+            const uint32_t row = row0 + j;
+            if (s > st.thr && row < row_end) {
+                const uint32_t id = row_ids ? static_cast<uint32_t>(__ldg(row_ids + row)) : row;
+                if constexpr (E > 0) {
+                    st.buf[st.cnt++] = make_key(s, id);
+                } else {
+                    // top-1: ids are not visited in increasing order here, so ties go through the key
+                    const uint64_t key = make_key(s, id);
+                    if (key > st.best) st.best = key;
+                    st.thr = key_score(st.best);
+                }
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, int STAGES, int E>
+__global__ void __launch_bounds__(256, 1)
+gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                         const GroupedParams p) {
+    constexpr int BLOCK_M = 128;
+    constexpr int BLOCK_K = 64;
+    constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(2 * BLOCK_N <= 512 && BLOCK_N % 32 == 0, "two accumulators must fit TMEM");
+    constexpr int C = 32 * (E > 0 ? E : 1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+            const GroupItem it = p.items[w];
+            const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
+            for (int t = 0; t < n_tiles; ++t) {
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one_sync()) {
+                        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+                        tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES, kb * BLOCK_K, it.a_row0, kEvictNormal);
+                        tma_load_2d(&tmap_x, &full_bar[stage], smem_b + stage * B_BYTES, kb * BLOCK_K,
+                                    it.x_row0 + t * BLOCK_N, kEvictNormal);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+            const GroupItem it = p.items[w];
+            const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
+            for (int t = 0; t < n_tiles; ++t) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
+                        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+                        const int nk = min(4, p.k16 - 4 * kb);
+                        for (int kk = 0; kk < nk; ++kk)
+                            umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == p.nkb - 1) umma_commit(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ----------------------------------------------------------- epilogue
+        const int ewarp = warp - 4;
+        const uint32_t lane_base = static_cast<uint32_t>(ewarp * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        LaneTopk<E> st;
+        uint64_t* warp_buf = p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C;
+        if constexpr (E > 0) st.buf = warp_buf + static_cast<size_t>(lane) * C;
+        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+            const GroupItem it = p.items[w];
+            const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
+            const int a_local = ewarp * 32 + static_cast<int>(lane);
+            const bool valid = a_local < it.a_rows;
+            const int a_row = it.a_row0 + a_local;
+            const int query = valid ? __ldg(p.pair_query + a_row) : 0;
+            const int dst = valid ? __ldg(p.pair_dst + a_row) : -1;
+            // ---- reset the selection state; the threshold starts from what other probes of the query found
+            st.gq = valid ? p.gthr + query : nullptr;
+            st.thr = valid ? thr_from_shared(__ldcg(st.gq)) : INFINITY;  // invalid lanes never collect
+            if constexpr (E > 0) {
+                st.cnt = 0;
+                for (int i = lane; i < 32 * C; i += 32) warp_buf[i] = 0;
+                __syncwarp();
+            } else {
+                st.best = 0;
+            }
+            const uint32_t row_end = static_cast<uint32_t>(it.x_row0 + it.x_rows);
+            for (int t = 0; t < n_tiles; ++t) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t row0 = static_cast<uint32_t>(it.x_row0 + t * BLOCK_N);
+                const uint32_t taddr = tmem_base + lane_base + acc * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
+                    tmem_ld_wait();
+                    if (c + 32 == BLOCK_N) {
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    scan_chunk_grouped<E>(st, v, row0 + c, row_end, p.row_ids, p.k);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            // ---- flush: part[dst][0..k)
+            if constexpr (E > 0) {
+                __syncwarp();
+                for (int l = 0; l < 32; ++l) {
+                    const int dst_l = __shfl_sync(0xffffffffu, dst, l);
+                    if (dst_l < 0) continue;  // warp-uniform
+                    uint64_t* b = warp_buf + static_cast<size_t>(l) * C;
+                    uint64_t key[E];
+                    const uint64_t kth = warp_compact<E>(b, p.k, key);
+                    if (static_cast<int>(lane) == l && kth != 0) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
+                    uint64_t* out = p.part + static_cast<size_t>(dst_l) * p.k;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int pos = e * 32 + lane;
+                        if (pos < p.k) out[pos] = key[e];
+                    }
+                }
+                __syncwarp();
+            } else {
+                if (valid) {
+                    p.part[dst] = st.best;
+                    if (st.best != 0) atomicMax(st.gq, static_cast<uint32_t>(st.best >> 32));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, TMEM_COLS);
+}
+
+// ===========================================================================
 // CTA pair (cta_group::2, M = 256) with the QUERIES RESIDENT ON CHIP.
 //
 //   * a cluster of two CTAs (one SM pair) owns 256 queries; each CTA keeps its

@@ -108,6 +108,18 @@ int cvdb_index_last_work(cvdb_index_t idx, double* flops, double* db_bytes, int*
  * 3 = CTA-pair streaming kernel, 4 = CTA-pair kernel with all of K <= 768 in TMEM (64-column accumulators) */
 int cvdb_index_last_variant(cvdb_index_t idx);
 
+/* -- inverted lists (IVF) on top of the coarse quantizer -------------------------
+ * cvdb_index_group_rows re-stores the rows list-major: stored position p receives the row that is currently at
+ * position perm[p]; row_ids[p] is the caller-visible id reported for position p; list_offsets [nlist+1] are the
+ * list boundaries in stored positions.  All three are DEVICE pointers (int32).  bf16 storage only.  add() after
+ * grouping un-groups the index (the caller re-groups).
+ * cvdb_index_search_lists: like cvdb_index_search, but query i only scans the lists probes[i][0..nprobe)
+ * (int32, follows on_device; entries < 0 are skipped).  Returned ids are row_ids values. */
+int cvdb_index_group_rows(cvdb_index_t idx, const int32_t* perm, const int32_t* row_ids, const int32_t* list_offsets,
+                          int nlist, void* stream);
+int cvdb_index_search_lists(cvdb_index_t idx, const void* q, int64_t nq, int dtype, int k, const int32_t* probes,
+                            int nprobe, float* D, int64_t* I, int on_device, void* stream);
+
 /* -- shard/merge layer ----------------------------------------------------
  * k-way select over `nlists` per-shard result lists, laid out [nlists][nq][k_in]
  * (what an all-gather of per-rank (D, I) produces).  Output [nq][k]. */

@@ -166,3 +166,29 @@ def test_synth_rows_chunk_invariance():
     b = O.synth_rows(1234, 65000, 66000, 8)
     assert np.array_equal(a[65000:66000], b)
     assert np.allclose(np.linalg.norm(a[:100], axis=1), 1.0, atol=1e-5)
+
+
+def test_ivf_oracle_consistency():
+    rng = np.random.default_rng(6)
+    n, d, nlist, nq, k = 800, 12, 9, 14, 6
+    xb, xq = rand_unit(rng, n, d), rand_unit(rng, nq, d)
+    cent = xb[:nlist].copy()
+    for metric in (O.METRIC_IP, O.METRIC_L2):
+        a = O.ivf_assign_ref(cent, xb, metric)
+        assert a.min() >= 0 and a.max() < nlist
+        # probing every list == brute force
+        allp = np.tile(np.arange(nlist), (nq, 1))
+        D, I = O.ivf_search_ref(xb, a, xq, k, allp, metric)
+        D_ref, I_ref = O.search_ref(xb, xq, k, metric)
+        assert np.array_equal(I, I_ref) and np.allclose(D, D_ref, atol=1e-6)
+        # a single probed list only returns rows of that list, in oracle order
+        probes = O.ivf_probe_ref(cent, xq, 2, metric)
+        D, I = O.ivf_search_ref(xb, a, xq, k, probes, metric)
+        for i in range(nq):
+            got = I[i][I[i] >= 0]
+            assert np.all(np.isin(a[got], probes[i]))
+            member = np.nonzero(np.isin(a, probes[i]))[0]
+            assert len(got) == min(k, len(member))
+        # skipped probes (-1) and empty result padding
+        D, I = O.ivf_search_ref(xb, a, xq[:2], k, np.full((2, 3), -1), metric)
+        assert (I == -1).all()
