@@ -324,6 +324,39 @@ __global__ void ivf_scatter_pairs_kernel(const int32_t* __restrict__ probes, int
     for (int c = lane; c < row_vec16; c += 32) dst[c] = src[c];
 }
 
+// ---------------------------------------------------------------------------
+// Triplet assembly from mined neighbours (README.md:2 "dataset of triplets"):
+// anchor i, its positive pos[i], and up to `per_anchor` hard negatives taken
+// from ranks [skip_top, ...) of the anchor's mined list, keeping only rows whose
+// score is on the "not a false negative" side of `limit`
+// (IP: score <= limit, L2: distance >= limit).  Fixed-stride output
+// [n][per_anchor][3] int64, unused slots are -1: no compaction, deterministic.
+// ---------------------------------------------------------------------------
+__global__ void build_triplets_kernel(const int64_t* __restrict__ I, const float* __restrict__ D, int64_t n, int k,
+                                      const int64_t* __restrict__ pos, int64_t anchor_base, int skip_top,
+                                      int per_anchor, int l2, float limit, int use_limit,
+                                      int64_t* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t* o = out + i * per_anchor * 3;
+    int w = 0;
+    const int64_t p = pos[i];
+    if (p >= 0) {
+        for (int r = skip_top; r < k && w < per_anchor; ++r) {
+            const int64_t id = I[i * k + r];
+            if (id < 0) break;
+            const float s = D[i * k + r];
+            if (use_limit && (l2 ? (s < limit) : (s > limit))) continue;
+            if (id == p) continue;
+            o[3 * w] = anchor_base + i;
+            o[3 * w + 1] = p;
+            o[3 * w + 2] = id;
+            ++w;
+        }
+    }
+    for (; w < per_anchor; ++w) { o[3 * w] = -1; o[3 * w + 1] = -1; o[3 * w + 2] = -1; }
+}
+
 // Exact-mode rescoring: recompute the score of each returned row from the
 // three bf16 planes (their sum reproduces the fp32 value) with fp32 FMAs, so
 // the reported distance does not carry tensor-core accumulation order effects.

@@ -931,6 +931,56 @@ int cvdb_index_search_lists(cvdb_index_t h, const void* q, int64_t nq, int dtype
     return CVDB_OK;
 }
 
+int cvdb_build_triplets(const int64_t* I, const float* D, int64_t n, int k, const int64_t* pos, int64_t anchor_base,
+                        int skip_top, int per_anchor, int metric, float limit, int use_limit, int64_t* out, void* stream) {
+    if (n < 0 || k < 1 || skip_top < 0 || per_anchor < 1) return fail(CVDB_EINVAL, "bad sizes");
+    if (metric != CVDB_METRIC_IP && metric != CVDB_METRIC_L2) return fail(CVDB_EINVAL, "unknown metric %d", metric);
+    if (n == 0) return CVDB_OK;
+    if (!I || !D || !pos || !out) return fail(CVDB_EINVAL, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    build_triplets_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(I, D, n, k, pos, anchor_base, skip_top,
+                                                                                    per_anchor, metric == CVDB_METRIC_L2,
+                                                                                    limit, use_limit, out);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+int64_t cvdb_index_row_bytes(cvdb_index_t h) { return h ? int64_t(reinterpret_cast<Index*>(h)->row_elems) * 2 : -1; }
+
+int cvdb_index_export_rows(cvdb_index_t h, int64_t row0, int64_t nrows, void* host_dst, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (row0 < 0 || nrows < 0 || row0 + nrows > ix->ntotal) return fail(CVDB_EINVAL, "row range outside the index");
+    if (nrows == 0) return CVDB_OK;
+    if (!host_dst) return fail(CVDB_EINVAL, "null pointer");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t rb = static_cast<size_t>(ix->row_elems) * 2;
+    CU_TRY(cudaMemcpyAsync(host_dst, reinterpret_cast<const char*>(ix->x) + row0 * rb, nrows * rb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return CVDB_OK;
+}
+
+int cvdb_index_import_rows(cvdb_index_t h, const void* host_src, int64_t nrows, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (nrows < 0) return fail(CVDB_EINVAL, "nrows < 0");
+    if (nrows == 0) return CVDB_OK;
+    if (!host_src) return fail(CVDB_EINVAL, "null pointer");
+    if (ix->ntotal + nrows > 0x7FFFFF00LL) return fail(CVDB_ELIMIT, "an index holds fewer than 2^31 rows per GPU");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(grow(ix, ix->ntotal + nrows, st));
+    const size_t rb = static_cast<size_t>(ix->row_elems) * 2;
+    CU_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(ix->x) + ix->ntotal * rb, host_src, nrows * rb, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    ix->ntotal += nrows;
+    ix->has_groups = false;
+    ix->grouped = false;
+    return CVDB_OK;
+}
+
 int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric, float* D,
                     int64_t* I, int on_device, void* stream) {
     if (nq < 0 || nlists < 1 || k_in < 1 || k < 1) return fail(CVDB_EINVAL, "bad sizes");

@@ -13,6 +13,7 @@ container kind and place as the queries.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -199,6 +200,59 @@ class IndexFlat:
         if b.kind == "torch":
             return torch.from_numpy(An), (torch.from_numpy(Dn) if return_dist else None)
         return An, Dn
+
+    # -- persistence -----------------------------------
+    def save(self, path: str, chunk_rows: int = 1 << 20) -> None:
+        """Dump the packed rows (exactly as stored in HBM) plus a small JSON header."""
+        import json
+        rb = int(_C.lib().cvdb_index_row_bytes(self._h))
+        n = self.ntotal
+        header = json.dumps({"format": "cvdb_b200.flat.v1", "d": self._d, "metric": self.metric,
+                             "storage": self.storage, "ntotal": n, "row_bytes": rb}).encode()
+        with open(path, "wb") as f:
+            f.write(len(header).to_bytes(8, "little"))
+            f.write(header)
+            buf = np.empty((min(chunk_rows, max(n, 1)), rb), np.uint8)
+            for r0 in range(0, n, chunk_rows):
+                m = min(chunk_rows, n - r0)
+                _C.check(_C.lib().cvdb_index_export_rows(self._h, r0, m, buf.ctypes.data, None))
+                f.write(buf[:m].tobytes())
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, chunk_rows: int = 1 << 20):
+        import json
+        with open(path, "rb") as f:
+            hl = int.from_bytes(f.read(8), "little")
+            h = json.loads(f.read(hl))
+            if h.get("format") != "cvdb_b200.flat.v1":
+                raise ValueError("not a cvdb_b200 index file")
+            idx = IndexFlat(h["d"], h["metric"], h["storage"], device)
+            rb, n = h["row_bytes"], h["ntotal"]
+            if rb != int(_C.lib().cvdb_index_row_bytes(idx._h)):
+                raise ValueError("row layout of the file does not match this build")
+            idx.reserve(n)
+            for r0 in range(0, n, chunk_rows):
+                m = min(chunk_rows, n - r0)
+                buf = np.frombuffer(f.read(m * rb), np.uint8)
+                if buf.size != m * rb:
+                    raise ValueError("truncated index file")
+                _C.check(_C.lib().cvdb_index_import_rows(idx._h, buf.ctypes.data, m, None))
+        return idx
+
+    def add_from_file(self, path: str, dtype: str = "float32", chunk_rows: int = 1 << 18, offset: int = 0) -> int:
+        """Streaming add() of a raw row-major [n, d] matrix on disk (float32 or bfloat16), memory-mapped
+        and fed in chunks so the corpus never has to be resident on the host.  Returns the rows added."""
+        esz = {"float32": 4, "bfloat16": 2}[dtype]
+        size = os.path.getsize(path) - offset
+        if size % (esz * self._d):
+            raise ValueError("file size is not a whole number of rows")
+        n = size // (esz * self._d)
+        mm = np.memmap(path, dtype=np.float32 if esz == 4 else np.uint16, mode="r", offset=offset, shape=(n, self._d))
+        for r0 in range(0, n, chunk_rows):
+            blk = np.ascontiguousarray(mm[r0:r0 + chunk_rows])
+            code = _C.DTYPE_F32 if esz == 4 else _C.DTYPE_BF16
+            _C.check(_C.lib().cvdb_index_add(self._h, blk.ctypes.data, blk.shape[0], code, 0, None))
+        return int(n)
 
     # -- measurement hooks ---------------------------------------------------
     def last_kernel_ms(self) -> float:

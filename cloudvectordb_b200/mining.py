@@ -8,6 +8,7 @@ from typing import Optional
 
 import numpy as np
 
+from . import _C
 from .index import IndexFlat, _is_torch
 
 try:
@@ -93,3 +94,31 @@ def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, 
     if not outs_d:
         return (torch.empty((0, k), dtype=torch.float32, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
     return torch.cat(outs_d), torch.cat(outs_i)
+
+
+def build_triplets(D, I, positives, *, skip_top: int = 0, per_anchor: int = 1, metric: str = "ip",
+                   limit: Optional[float] = None, anchor_base: int = 0):
+    """(anchor, positive, hard negative) triplets from mined neighbours.
+
+    D, I        [n, k] as returned by mine_hard_negatives (positives and the anchor already excluded)
+    positives   [n] id of one positive per anchor (< 0: the anchor yields no triplet)
+    skip_top    ignore the first ranks (the very closest rows are often unlabeled positives)
+    limit       drop rows scoring above it (IP) / closer than it (L2): a margin against false negatives
+    returns     int64 [n, per_anchor, 3]; unused slots are -1.  Runs on the GPU (cvdb_build_triplets)."""
+    as_numpy = not _is_torch(I)
+    dev = I.device if (_is_torch(I) and I.is_cuda) else torch.device("cuda", torch.cuda.current_device())
+    It = torch.as_tensor(I).to(dev, torch.int64).contiguous()
+    Dt = torch.as_tensor(D).to(dev, torch.float32).contiguous()
+    pt = torch.as_tensor(positives).to(dev, torch.int64).contiguous()
+    n, k = It.shape
+    if pt.numel() != n:
+        raise ValueError("positives must have one entry per anchor")
+    out = torch.empty((n, per_anchor, 3), dtype=torch.int64, device=dev)
+    metric_code = {"ip": _C.METRIC_IP, "l2": _C.METRIC_L2}[metric.lower()]
+    _C.check(_C.lib().cvdb_build_triplets(It.data_ptr(), Dt.data_ptr(), n, k, pt.data_ptr(), int(anchor_base),
+                                          int(skip_top), int(per_anchor), metric_code,
+                                          float(limit if limit is not None else 0.0), int(limit is not None),
+                                          out.data_ptr(), int(torch.cuda.current_stream(dev.index).cuda_stream)))
+    if as_numpy:
+        return out.cpu().numpy()
+    return out if (_is_torch(I) and I.is_cuda) else out.cpu()

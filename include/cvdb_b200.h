@@ -120,6 +120,21 @@ int cvdb_index_group_rows(cvdb_index_t idx, const int32_t* perm, const int32_t* 
 int cvdb_index_search_lists(cvdb_index_t idx, const void* q, int64_t nq, int dtype, int k, const int32_t* probes,
                             int nprobe, float* D, int64_t* I, int on_device, void* stream);
 
+/* -- triplet assembly from mined neighbours (README.md:2 "dataset of triplets") ---------
+ * For anchor i (global id anchor_base + i) with positive pos[i] (< 0: none), take up to per_anchor hard negatives
+ * from ranks [skip_top, k) of its mined list (I, D as returned by a search with exclusion), skipping rows on the
+ * "probably a false negative" side of `limit` when use_limit (IP: score > limit, L2: distance < limit).
+ * out [n][per_anchor][3] int64 = (anchor, positive, negative), unused slots -1.  Device pointers only. */
+int cvdb_build_triplets(const int64_t* I, const float* D, int64_t n, int k, const int64_t* pos, int64_t anchor_base,
+                        int skip_top, int per_anchor, int metric, float limit, int use_limit, int64_t* out, void* stream);
+
+/* -- persistence: the packed rows as stored in HBM (row_bytes each), to / from HOST memory ------------
+ * A file written from export_rows can be re-loaded with import_rows into an index created with the same
+ * (d, metric, storage).  Rows keep their order; groups / list grouping are not part of the dump. */
+int64_t cvdb_index_row_bytes(cvdb_index_t idx);
+int cvdb_index_export_rows(cvdb_index_t idx, int64_t row0, int64_t nrows, void* host_dst, void* stream);
+int cvdb_index_import_rows(cvdb_index_t idx, const void* host_src, int64_t nrows, void* stream);
+
 /* -- shard/merge layer ----------------------------------------------------
  * k-way select over `nlists` per-shard result lists, laid out [nlists][nq][k_in]
  * (what an all-gather of per-rank (D, I) produces).  Output [nq][k]. */

@@ -192,3 +192,13 @@ def test_ivf_oracle_consistency():
         # skipped probes (-1) and empty result padding
         D, I = O.ivf_search_ref(xb, a, xq[:2], k, np.full((2, 3), -1), metric)
         assert (I == -1).all()
+
+
+def test_triplet_oracle_rules():
+    I = np.array([[5, 6, 7, 8], [9, -1, -1, -1], [1, 2, 3, 4]], np.int64)
+    D = np.array([[.9, .8, .7, .6], [.5, 0, 0, 0], [.4, .3, .2, .1]], np.float32)
+    pos = np.array([6, 3, -1], np.int64)
+    T = O.build_triplets_ref(D, I, pos, skip_top=0, per_anchor=2, metric=O.METRIC_IP, limit=0.85, anchor_base=10)
+    assert T[0].tolist() == [[10, 6, 7], [10, 6, 8]]     # 5 is above the limit, 6 is the positive itself
+    assert T[1].tolist() == [[11, 3, 9], [-1, -1, -1]]   # list ends at the first -1
+    assert (T[2] == -1).all()                            # no positive -> no triplet
