@@ -424,6 +424,24 @@ def test_large_database_properties():
     assert torch.equal(Im, I) and torch.equal(Dm, D)
 
 
+def test_query_batches_larger_than_one_launch_are_chunked():
+    """More than 65 536 queries (262 144 for k = 1) go through several launches inside one call."""
+    rng = np.random.default_rng(91)
+    n, d = 3000, 32
+    xb = O.bf16_round(unit_rows(rng, n, d))
+    for nq, k in ((70_000, 5), (270_000, 1)):
+        xq = O.bf16_round(unit_rows(rng, nq, d))
+        D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_IP)
+        idx = make_index(d, "ip", "bf16")
+        idx.add(xb)
+        D, I = idx.search(xq, k)
+        if k == 1:
+            A, dist = idx.assign(torch.from_numpy(xq).cuda())
+            assert np.array_equal(A.cpu().numpy(), I[:, 0])
+        idx.close()
+        assert_parity(D, I, D_ref, I_ref, "ip", tie_tol=2e-5)
+
+
 def test_errors_are_reported_not_swallowed():
     from cloudvectordb_b200 import _C
     idx = make_index(16, "ip", "bf16")
