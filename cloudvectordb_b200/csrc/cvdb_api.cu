@@ -15,7 +15,7 @@
 #include <string>
 
 #include "aux_kernels.cuh"
-#include "gemm_topk.cuh"
+#include "launchers.h"
 
 namespace {
 
@@ -196,7 +196,6 @@ int pack_dispatch(const void* in, int dtype, int64_t n, __nv_bfloat16* out, cons
 
 // ------------------------------------------------------- kernel selection
 constexpr int kBlockN = 256;
-constexpr int kStages = 4;
 
 int pick_E(int k) {
     if (k == 1) return 0;
@@ -229,65 +228,13 @@ void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& 
     }
 }
 
-template <int E>
-int launch_gemm_topk(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid, cudaStream_t st) {
-    auto kern = gemm_topk_ss_kernel<kBlockN, kStages, E>;
-    constexpr size_t smem = gemm_topk_ss_smem_bytes<kBlockN, kStages>();
-    static bool configured = false;
-    if (!configured) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
-    kern<<<grid, 256, smem, st>>>(tq, tx, p);
-    ++g_launches;
-    CU_TRY(cudaGetLastError());
-    return CVDB_OK;
-}
-
-template <int E>
-int launch_gemm_topk_ss2(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid, cudaStream_t st) {
-    auto kern = gemm_topk_ss2_kernel<256, 6, E>;
-    constexpr size_t smem = gemm_topk_ss2_smem_bytes<256, 6>();
-    static bool configured = false;
-    if (!configured) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
-    kern<<<grid, 256, smem, st>>>(tq, tx, p);
-    ++g_launches;
-    CU_TRY(cudaGetLastError());
-    return CVDB_OK;
-}
-
-template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES, int E>
-int launch_gemm_topk_ts2(const CUtensorMap& tx, const CUtensorMap& tq, const __nv_bfloat16* q_pack, int q_row_elems,
-                         const GemmTopkParams& p, int grid, cudaStream_t st) {
-    auto kern = gemm_topk_ts2_kernel<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, E>;
-    constexpr size_t smem = gemm_topk_ts2_smem_bytes<BLOCK_N, KB_S, KB_STAGE, STAGES>();
-    static_assert(smem <= 232448, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
-    kern<<<grid, 256, smem, st>>>(tx, tq, q_pack, q_row_elems, p);
-    ++g_launches;
-    CU_TRY(cudaGetLastError());
-    return CVDB_OK;
-}
-
-template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES>
-int dispatch_ts2(int E, const CUtensorMap& tx, const CUtensorMap& tq, const __nv_bfloat16* q_pack, int q_row_elems,
-                 const GemmTopkParams& p, int grid, cudaStream_t st) {
-    switch (E) {
-        case 0: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 0>(tx, tq, q_pack, q_row_elems, p, grid, st);
-        case 1: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 1>(tx, tq, q_pack, q_row_elems, p, grid, st);
-        case 2: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 2>(tx, tq, q_pack, q_row_elems, p, grid, st);
-        case 4: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 4>(tx, tq, q_pack, q_row_elems, p, grid, st);
-        case 8: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 8>(tx, tq, q_pack, q_row_elems, p, grid, st);
-        default: return launch_gemm_topk_ts2<BLOCK_N, KB_T, KB_S, KB_STAGE, STAGES, 16>(tx, tq, q_pack, q_row_elems, p, grid, st);
-    }
-}
+// translate a launcher's cudaError_t
+#define LAUNCH(expr)                                                                                        \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        ++g_launches;                                                                                       \
+        if (e_ != cudaSuccess) return fail(CVDB_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
 
 // Core: search `nq` packed-on-the-fly queries against the whole index.
 // Outputs are device pointers: D [nq][k] f32 and either I64 or I32 [nq][k].
@@ -409,32 +356,14 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         CU_TRY(cudaEventRecord(ix->ev0[slot], st));
     }
     if (variant == 4) {
-        TRY((dispatch_ts2<64, 12, 0, 12, 4>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+        LAUNCH(launch_ts2(3, E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st));
     } else if (variant == 2) {
-        if (p.nkb <= 8)
-            TRY((dispatch_ts2<128, 8, 0, 4, 6>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
-        else if (p.nkb <= 12)
-            TRY((dispatch_ts2<128, 8, 4, 4, 5>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
-        else  // 13 K blocks: d = 768 with the three L2 norm columns
-            TRY((dispatch_ts2<128, 8, 5, 5, 3>(E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st)));
+        const int cfg = p.nkb <= 8 ? 0 : (p.nkb <= 12 ? 1 : 2);  // all of K in TMEM / + 4-block tail / + 5-block tail
+        LAUNCH(launch_ts2(cfg, E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st));
     } else if (variant == 3) {
-        switch (E) {
-            case 0: TRY(launch_gemm_topk_ss2<0>(tq, tx, p, grid, st)); break;
-            case 1: TRY(launch_gemm_topk_ss2<1>(tq, tx, p, grid, st)); break;
-            case 2: TRY(launch_gemm_topk_ss2<2>(tq, tx, p, grid, st)); break;
-            case 4: TRY(launch_gemm_topk_ss2<4>(tq, tx, p, grid, st)); break;
-            case 8: TRY(launch_gemm_topk_ss2<8>(tq, tx, p, grid, st)); break;
-            default: TRY(launch_gemm_topk_ss2<16>(tq, tx, p, grid, st)); break;
-        }
+        LAUNCH(launch_ss2(E, tq, tx, p, grid, st));
     } else {
-        switch (E) {
-            case 0: TRY(launch_gemm_topk<0>(tq, tx, p, grid, st)); break;
-            case 1: TRY(launch_gemm_topk<1>(tq, tx, p, grid, st)); break;
-            case 2: TRY(launch_gemm_topk<2>(tq, tx, p, grid, st)); break;
-            case 4: TRY(launch_gemm_topk<4>(tq, tx, p, grid, st)); break;
-            case 8: TRY(launch_gemm_topk<8>(tq, tx, p, grid, st)); break;
-            default: TRY(launch_gemm_topk<16>(tq, tx, p, grid, st)); break;
-        }
+        LAUNCH(launch_ss1(E, tq, tx, p, grid, st));
     }
     if (prof) {
         CU_TRY(cudaEventRecord(ix->ev1[slot], st));
@@ -473,22 +402,6 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
 
 static_assert(sizeof(IvfItem) == sizeof(GroupItem), "item layouts must agree");
 constexpr int kGroupedBlockN = 128;
-constexpr int kGroupedStages = 6;
-
-template <int E>
-int launch_grouped(const CUtensorMap& tq, const CUtensorMap& tx, const GroupedParams& p, int grid, cudaStream_t st) {
-    auto kern = gemm_topk_grouped_kernel<kGroupedBlockN, kGroupedStages, E>;
-    constexpr size_t smem = gemm_topk_ss_smem_bytes<kGroupedBlockN, kGroupedStages>();
-    static bool configured = false;
-    if (!configured) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
-    kern<<<grid, 256, smem, st>>>(tq, tx, p);
-    ++g_launches;
-    CU_TRY(cudaGetLastError());
-    return CVDB_OK;
-}
 
 // Search `nq` queries, each restricted to the `nprobe` inverted lists named in probes[nq][nprobe]
 // (device pointers; D/I device outputs).
@@ -560,14 +473,7 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
         CUtensorMap tq, tx;
         TRY(make_tmap_2d(&tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 128));
         TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, kGroupedBlockN));
-        switch (E) {
-            case 0: TRY(launch_grouped<0>(tq, tx, p, grid, st)); break;
-            case 1: TRY(launch_grouped<1>(tq, tx, p, grid, st)); break;
-            case 2: TRY(launch_grouped<2>(tq, tx, p, grid, st)); break;
-            case 4: TRY(launch_grouped<4>(tq, tx, p, grid, st)); break;
-            case 8: TRY(launch_grouped<8>(tq, tx, p, grid, st)); break;
-            default: TRY(launch_grouped<16>(tq, tx, p, grid, st)); break;
-        }
+        LAUNCH(launch_grouped(E, tq, tx, p, grid, st));
     }
     ix->last_flops = 0;
     ix->last_slices = nprobe;
