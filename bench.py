@@ -310,6 +310,29 @@ def run_ours(a):
     ref_i = best_i.cpu().numpy()
     got_i = torch.as_tensor(I)[:nchk].cpu().numpy()
     recall = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, ref_i)]))
+
+    # the same against fp32 scores of the UNROUNDED fp32 rows and queries (regenerated chunk by chunk)
+    qs32 = gen_rows(torch, dev, Q_SEED, 0, nchk, a.dim, torch.float32)
+    bv = torch.full((nchk, a.k), -float("inf"), device=dev)
+    bi = torch.full((nchk, a.k), -1, dtype=torch.int64, device=dev)
+    for r0 in range(lo, hi, 1 << 20):
+        blk = gen_rows(torch, dev, DB_SEED, r0, min(hi, r0 + (1 << 20)), a.dim, torch.float32)
+        s = qs32 @ blk.T
+        if a.metric == "l2":
+            s = -((qs32 * qs32).sum(1)[:, None] - 2 * s + (blk * blk).sum(1)[None, :])
+        v, i = torch.topk(s, min(a.k, blk.shape[0]), dim=1)
+        cv, ci = torch.cat([bv, v], 1), torch.cat([bi, i + r0], 1)
+        o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :a.k]
+        bv, bi = torch.gather(cv, 1, o), torch.gather(ci, 1, o)
+    if world > 1:
+        gv = [torch.empty_like(bv) for _ in range(world)]
+        gi = [torch.empty_like(bi) for _ in range(world)]
+        dist.all_gather(gv, bv)
+        dist.all_gather(gi, bi)
+        cv, ci = torch.cat(gv, 1), torch.cat(gi, 1)
+        o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :a.k]
+        bi = torch.gather(ci, 1, o)
+    recall32 = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, bi.cpu().numpy())]))
     same_e2e = bool(np.array_equal(torch.as_tensor(Ih)[:nchk].cpu().numpy(), got_i))
 
     cpu_base = None
@@ -331,6 +354,7 @@ def run_ours(a):
             "roofline": roofline,
             "cpu_baseline": cpu_base,
             "recall_at_k_vs_fp32_torch_on_same_bf16_values": recall,
+            "recall_at_k_vs_fp32_torch_on_unrounded_fp32_inputs": recall32,
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
