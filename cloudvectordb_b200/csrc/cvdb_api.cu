@@ -774,16 +774,25 @@ int cvdb_index_group_rows(cvdb_index_t h, const int32_t* perm, const int32_t* ro
     __nv_bfloat16* nx = nullptr;
     cudaError_t e = cudaMalloc(&nx, bytes);
     if (e != cudaSuccess) return fail(CVDB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    int rc = ix->row_ids.ensure(static_cast<size_t>(ix->ntotal) * 4);
+    if (rc == CVDB_OK) rc = ix->list_off.ensure(static_cast<size_t>(nlist + 1) * 4);
+    if (rc != CVDB_OK) {
+        cudaFree(nx);
+        return rc;
+    }
     const int64_t blocks = std::min<int64_t>(ceil_div(ix->ntotal, 8), 148 * 32);
     permute_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(ix->x), perm,
                                                                          ix->ntotal, ix->row_elems * 2 / 16,
                                                                          reinterpret_cast<uint4*>(nx));
     ++g_launches;
-    TRY(ix->row_ids.ensure(static_cast<size_t>(ix->ntotal) * 4));
-    TRY(ix->list_off.ensure(static_cast<size_t>(nlist + 1) * 4));
-    CU_TRY(cudaMemcpyAsync(ix->row_ids.p, row_ids, static_cast<size_t>(ix->ntotal) * 4, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(cudaMemcpyAsync(ix->list_off.p, list_offsets, static_cast<size_t>(nlist + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    e = cudaMemcpyAsync(ix->row_ids.p, row_ids, static_cast<size_t>(ix->ntotal) * 4, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ix->list_off.p, list_offsets, static_cast<size_t>(nlist + 1) * 4, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(nx);
+        return fail(CVDB_ECUDA, "regrouping the rows failed: %s", cudaGetErrorString(e));
+    }
     cudaFree(ix->x);
     ix->x = nx;
     ix->capacity = ix->ntotal;

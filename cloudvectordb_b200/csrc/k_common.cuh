@@ -5,12 +5,18 @@
 
 namespace cvdb {
 
+// `configured` is a per-kernel bit mask over device ordinals: the opt-in to > 48 KB of dynamic shared
+// memory is a per-device function attribute.
 template <typename Kern, typename... Args>
-cudaError_t launch_kernel(Kern kern, size_t smem, bool& configured, int grid, cudaStream_t st, Args... args) {
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured, int grid, cudaStream_t st, Args... args) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured & bit)) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured |= bit;
     }
     kern<<<grid, 256, smem, st>>>(args...);
     return cudaGetLastError();

@@ -455,3 +455,47 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(_C.CvdbError):
         idx.search(np.ones((2, 16), np.float32), 3, group_q=np.zeros(2, np.int32))   # no groups set
     idx.close()
+
+
+# ---- seeded fuzz over shapes, k boundaries, metrics, storages and kernel variants ------------------------
+def _fuzz_cases():
+    rng = np.random.default_rng(20261018)
+    edge_k = [1, 2, 12, 13, 28, 29, 60, 61, 124, 125, 200, 504]
+    edge_n = [1, 127, 128, 129, 255, 256, 257, 511, 513, 1000, 4099]
+    edge_q = [1, 2, 127, 128, 129, 255, 256, 257, 300, 513]
+    edge_d = [1, 3, 8, 13, 61, 64, 65, 125, 128, 200, 384, 509, 512, 515, 765, 768, 829]
+    cases = []
+    for i in range(60):
+        d = int(rng.choice(edge_d))
+        n = int(rng.choice(edge_n)) if i % 3 else int(rng.integers(1, 9000))
+        nq = int(rng.choice(edge_q)) if i % 2 else int(rng.integers(1, 700))
+        k = int(rng.choice(edge_k))
+        metric = "ip" if rng.random() < 0.5 else "l2"
+        storage = "exact" if (i % 5 == 4 and d <= 256) else "bf16"
+        variant = int(rng.choice([0, 1, 2, 3, 4])) if storage == "bf16" else int(rng.choice([0, 1, 3]))
+        padded = d + (3 if metric == "l2" else 0)
+        if variant == 4 and padded > 768:
+            variant = 2
+        if variant in (2, 4) and padded > 832:
+            variant = 1
+        cases.append((i, metric, storage, variant, n, d, nq, k))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: f"{c[0]}-{c[1]}-{c[2]}-v{c[3]}-n{c[4]}-d{c[5]}-q{c[6]}-k{c[7]}")
+def test_fuzz_against_oracle(case):
+    i, metric, storage, variant, n, d, nq, k = case
+    rng = np.random.default_rng(1000 + i)
+    xb, xq = unit_rows(rng, n, d), unit_rows(rng, nq, d)
+    if storage == "bf16":
+        xb, xq = O.bf16_round(xb), O.bf16_round(xq)
+    if i % 4 == 0 and n > 8:            # duplicated rows: ties must resolve to the lower id
+        xb[n // 2] = xb[1]
+        xb[n - 1] = xb[1]
+        xq[0] = xb[1]
+    D_ref, I_ref = O.search_ref(xb, xq, k, M[metric])
+    idx = make_index(d, metric, storage)
+    idx.add(xb)
+    D, I = idx.search(xq, k, force_variant=variant, force_slices=(i % 7) if i % 2 else 0)
+    idx.close()
+    assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5 if storage == "bf16" else 1e-5)
