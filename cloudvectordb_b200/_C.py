@@ -56,7 +56,8 @@ SIGNATURES = {
     "cvdb_index_last_work": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int)]),
     "cvdb_index_last_variant": (C.c_int, [C.c_void_p]),
-    "cvdb_index_group_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cvdb_index_group_by_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cvdb_index_list_offsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvdb_index_search_lists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cvdb_build_triplets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,

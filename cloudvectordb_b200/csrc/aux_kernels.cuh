@@ -237,6 +237,47 @@ __global__ void permute_rows_kernel(const uint4* __restrict__ in, const int32_t*
     }
 }
 
+// rows per list, for the rows as currently stored: list of stored row p = list_of_id[row_ids[p]]
+__global__ void ivf_count_rows_kernel(const int32_t* __restrict__ list_of_id, const int32_t* __restrict__ row_ids,
+                                      int64_t n, int nlist, int32_t* __restrict__ cnt, int32_t* __restrict__ bad) {
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int l = list_of_id[row_ids[p]];
+    if (l < 0 || l >= nlist) { atomicAdd(bad, 1); return; }
+    atomicAdd(cnt + l, 1);
+}
+
+// one warp per stored row: claim a slot in its list (order inside a list is arbitrary; candidate keys carry
+// the row id, so results do not depend on it) and move the packed row and its id there
+__global__ void ivf_scatter_rows_kernel(const int32_t* __restrict__ list_of_id, const int32_t* __restrict__ row_ids,
+                                        int64_t n, int nlist, const int32_t* __restrict__ list_off,
+                                        int32_t* __restrict__ cursor, const uint4* __restrict__ x_old, int row_vec16,
+                                        uint4* __restrict__ x_new, int32_t* __restrict__ row_ids_new) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (p >= n) return;
+    const int id = row_ids[p];
+    const int l = list_of_id[id];
+    if (l < 0 || l >= nlist) return;
+    int pos = 0;
+    if (lane == 0) pos = list_off[l] + atomicAdd(cursor + l, 1);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (lane == 0) row_ids_new[pos] = id;
+    const uint4* src = x_old + p * row_vec16;
+    uint4* dst = x_new + static_cast<int64_t>(pos) * row_vec16;
+    for (int c = lane; c < row_vec16; c += 32) dst[c] = src[c];
+}
+
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t first, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<int32_t>(first + i);
+}
+
+// list_off[l] = exclusive prefix (from the scan), list_off[nlist] = total
+__global__ void ivf_close_offsets_kernel(int32_t* __restrict__ list_off, int nlist, const int32_t* __restrict__ scal) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) list_off[nlist] = scal[1];
+}
+
 // (query, probe) pairs per list; pairs naming an invalid or empty list are dropped
 __global__ void ivf_count_pairs_kernel(const int32_t* __restrict__ probes, int64_t n_pairs, int nlist,
                                        const int32_t* __restrict__ list_off, int32_t* __restrict__ cnt) {

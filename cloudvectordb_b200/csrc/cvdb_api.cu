@@ -69,6 +69,26 @@ struct DevBuf {
         cap = want;
         return CVDB_OK;
     }
+    // grow to `bytes`, preserving the first `keep` bytes
+    int grow_keep(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap) return CVDB_OK;
+        void* np_ = nullptr;
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&np_, want);
+        if (e != cudaSuccess) return fail(CVDB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        if (p && keep) {
+            e = cudaMemcpyAsync(np_, p, keep, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                cudaFree(np_);
+                return fail(CVDB_ECUDA, "device copy failed: %s", cudaGetErrorString(e));
+            }
+        }
+        if (p) cudaFree(p);
+        p = np_;
+        cap = want;
+        return CVDB_OK;
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -123,6 +143,7 @@ struct Index {
     // inverted-list (IVF) layout: rows stored list-major after cvdb_index_group_rows
     bool grouped = false;
     int nlist = 0;
+    int64_t row_ids_n = 0;  // leading stored rows whose row_ids entry is valid (later rows: id == position)
     DevBuf row_ids, list_off, ivf_cnt, ivf_pair_off, ivf_item_off, ivf_cursor, ivf_scal, ivf_items, ivf_pair_query,
         ivf_pair_dst, ivf_qg, ivf_probes;
     DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
@@ -446,10 +467,8 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
         ix->ivf_qg.as<uint4>());
     g_launches += 4;
     CU_TRY(cudaGetLastError());
-    int32_t scal[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(scal, ix->ivf_scal.p, 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));  // the item count sizes the grid
-    const int n_items = scal[0];
+    // the item count stays on the device (the kernel reads it): no host synchronisation on this path
+    const int n_items = static_cast<int>(std::min<int64_t>(max_items, INT32_MAX));  // upper bound, sizes the grid
 
     TRY(ix->part.ensure(static_cast<size_t>(std::max<int64_t>(n_pairs, 1)) * k * 8));
     CU_TRY(cudaMemsetAsync(ix->part.p, 0, static_cast<size_t>(n_pairs) * k * 8, st));  // dropped pairs stay empty
@@ -459,7 +478,7 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
         const int grid = std::min(ix->num_sms, n_items);
         if (E > 0) TRY(ix->cand.ensure(static_cast<size_t>(grid) * 128 * C * 8));
         GroupedParams p{};
-        p.n_items = n_items;
+        p.n_items_ptr = ix->ivf_scal.as<int32_t>();
         p.k = k;
         p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
         p.k16 = static_cast<int>(ceil_div(ix->Kp, 16));
@@ -565,6 +584,7 @@ int cvdb_index_reset(cvdb_index_t h) {
     ix->ntotal = 0;
     ix->has_groups = false;
     ix->grouped = false;
+    ix->row_ids_n = 0;
     return CVDB_OK;
 }
 
@@ -641,7 +661,7 @@ int cvdb_index_search(cvdb_index_t h, const void* q, int64_t nq, int dtype, int 
     if (opts && opts->group_q && !ix->has_groups)
         return fail(CVDB_EINVAL, "group_q given but the index has no groups (cvdb_index_set_groups)");
     if (ix->grouped)
-        return fail(CVDB_EINVAL, "rows are stored list-major (cvdb_index_group_rows): use cvdb_index_search_lists");
+        return fail(CVDB_EINVAL, "rows are stored list-major (cvdb_index_group_by_list): use cvdb_index_search_lists");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
@@ -760,34 +780,55 @@ int cvdb_index_last_work(cvdb_index_t h, double* flops, double* db_bytes, int* n
 
 int cvdb_index_last_variant(cvdb_index_t h) { return h ? reinterpret_cast<Index*>(h)->last_variant : -1; }
 
-int cvdb_index_group_rows(cvdb_index_t h, const int32_t* perm, const int32_t* row_ids, const int32_t* list_offsets,
-                          int nlist, void* stream) {
+int cvdb_index_group_by_list(cvdb_index_t h, const int32_t* list_of_id, int nlist, void* stream) {
     TRY(check_index(h));
     Index* ix = reinterpret_cast<Index*>(h);
     if (ix->planes != 1) return fail(CVDB_EINVAL, "inverted lists need bf16 storage");
     if (nlist < 1) return fail(CVDB_EINVAL, "nlist < 1");
-    if (!perm || !row_ids || !list_offsets) return fail(CVDB_EINVAL, "null pointer");
+    if (!list_of_id) return fail(CVDB_EINVAL, "null pointer");
     if (ix->ntotal == 0) return fail(CVDB_EINVAL, "empty index");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t bytes = static_cast<size_t>(ix->ntotal) * ix->row_elems * 2;
+    const int64_t n = ix->ntotal;
+    const int row_vec16 = ix->row_elems * 2 / 16;
+    // ids of the rows as stored now: what an earlier grouping left, then insertion order for rows added since
+    TRY(ix->row_ids.grow_keep(static_cast<size_t>(n) * 4, static_cast<size_t>(ix->row_ids_n) * 4, st));
+    if (ix->row_ids_n < n) {
+        const int64_t m = n - ix->row_ids_n;
+        iota_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, st>>>(ix->row_ids.as<int32_t>() + ix->row_ids_n,
+                                                                              ix->row_ids_n, m);
+        ++g_launches;
+        ix->row_ids_n = n;
+    }
+    TRY(ix->ivf_cnt.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_cursor.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_item_off.ensure(static_cast<size_t>(nlist) * 4));
+    TRY(ix->ivf_scal.ensure(16));
+    TRY(ix->list_off.ensure(static_cast<size_t>(nlist + 1) * 4));
+    TRY(ix->ids_a.ensure(static_cast<size_t>(n) * 4));  // new row ids
+    CU_TRY(cudaMemsetAsync(ix->ivf_cnt.p, 0, static_cast<size_t>(nlist) * 4, st));
+    CU_TRY(cudaMemsetAsync(ix->ivf_cursor.p, 0, static_cast<size_t>(nlist) * 4, st));
+    CU_TRY(cudaMemsetAsync(ix->ivf_scal.p, 0, 16, st));
+    int32_t* bad = ix->ivf_scal.as<int32_t>() + 2;
+    ivf_count_rows_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(list_of_id, ix->row_ids.as<int32_t>(), n,
+                                                                                  nlist, ix->ivf_cnt.as<int32_t>(), bad);
+    ivf_scan_lists_kernel<<<1, 1024, 0, st>>>(ix->ivf_cnt.as<int32_t>(), nlist, ix->list_off.as<int32_t>(),
+                                               ix->ivf_item_off.as<int32_t>(), ix->ivf_scal.as<int32_t>());
+    ivf_close_offsets_kernel<<<1, 32, 0, st>>>(ix->list_off.as<int32_t>(), nlist, ix->ivf_scal.as<int32_t>());
+    g_launches += 3;
+    int32_t n_bad = 0;
+    CU_TRY(cudaMemcpyAsync(&n_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (n_bad) return fail(CVDB_EINVAL, "%d rows name a list outside [0, %d)", n_bad, nlist);
+    const size_t bytes = static_cast<size_t>(n) * ix->row_elems * 2;
     __nv_bfloat16* nx = nullptr;
     cudaError_t e = cudaMalloc(&nx, bytes);
     if (e != cudaSuccess) return fail(CVDB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-    int rc = ix->row_ids.ensure(static_cast<size_t>(ix->ntotal) * 4);
-    if (rc == CVDB_OK) rc = ix->list_off.ensure(static_cast<size_t>(nlist + 1) * 4);
-    if (rc != CVDB_OK) {
-        cudaFree(nx);
-        return rc;
-    }
-    const int64_t blocks = std::min<int64_t>(ceil_div(ix->ntotal, 8), 148 * 32);
-    permute_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(ix->x), perm,
-                                                                         ix->ntotal, ix->row_elems * 2 / 16,
-                                                                         reinterpret_cast<uint4*>(nx));
+    ivf_scatter_rows_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, st>>>(
+        list_of_id, ix->row_ids.as<int32_t>(), n, nlist, ix->list_off.as<int32_t>(), ix->ivf_cursor.as<int32_t>(),
+        reinterpret_cast<const uint4*>(ix->x), row_vec16, reinterpret_cast<uint4*>(nx), ix->ids_a.as<int32_t>());
     ++g_launches;
-    e = cudaMemcpyAsync(ix->row_ids.p, row_ids, static_cast<size_t>(ix->ntotal) * 4, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(ix->list_off.p, list_offsets, static_cast<size_t>(nlist + 1) * 4, cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyAsync(ix->row_ids.p, ix->ids_a.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         cudaFree(nx);
@@ -795,10 +836,21 @@ int cvdb_index_group_rows(cvdb_index_t h, const int32_t* perm, const int32_t* ro
     }
     cudaFree(ix->x);
     ix->x = nx;
-    ix->capacity = ix->ntotal;
+    ix->capacity = n;
     ix->grouped = true;
     ix->nlist = nlist;
     ix->has_groups = false;
+    return CVDB_OK;
+}
+
+int cvdb_index_list_offsets(cvdb_index_t h, int32_t* out_device, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix->grouped) return fail(CVDB_EINVAL, "rows are not grouped into lists");
+    if (!out_device) return fail(CVDB_EINVAL, "null pointer");
+    cvdb_guard g(ix->device);
+    CU_TRY(cudaMemcpyAsync(out_device, ix->list_off.p, static_cast<size_t>(ix->nlist + 1) * 4, cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(stream)));
     return CVDB_OK;
 }
 
@@ -806,7 +858,7 @@ int cvdb_index_search_lists(cvdb_index_t h, const void* q, int64_t nq, int dtype
                             float* D, int64_t* I, int on_device, void* stream) {
     TRY(check_index(h));
     Index* ix = reinterpret_cast<Index*>(h);
-    if (!ix->grouped) return fail(CVDB_EINVAL, "rows are not grouped into lists (cvdb_index_group_rows)");
+    if (!ix->grouped) return fail(CVDB_EINVAL, "rows are not grouped into lists (cvdb_index_group_by_list)");
     if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
     if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
     if (nprobe < 1 || nprobe > 4096) return fail(CVDB_ELIMIT, "nprobe=%d outside [1, 4096]", nprobe);

@@ -85,9 +85,12 @@ struct LaneTopk<0> {
 __device__ __forceinline__ float thr_from_shared(uint32_t g) {
     return g > 1u ? ordered_to_float(g - 1u) : -INFINITY;
 }
+// strict_own: rows still to come in this item have larger ids than everything collected so far (true for the
+// flat kernels, which walk rows in id order), so a score equal to the own k-th cannot displace it.
+template <bool strict_own = true>
 __device__ __forceinline__ float publish_and_refresh(uint32_t* gq, uint64_t kth, float thr) {
     const uint32_t ord = static_cast<uint32_t>(kth >> 32);  // 0 when fewer than k candidates exist
-    float t = ord ? ordered_to_float(ord) : -INFINITY;      // own k-th: later rows of this slice need strictly more
+    float t = ord ? (strict_own ? ordered_to_float(ord) : thr_from_shared(ord)) : -INFINITY;
     if (gq != nullptr) {
         const uint32_t old = atomicMax(gq, ord);
         if (old > ord) t = fmaxf(t, thr_from_shared(old));
@@ -112,7 +115,7 @@ __device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&
     return warp_sorted_at<E>(key, k - 1);
 }
 
-template <int E>
+template <int E, bool strict_own = true>
 __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
     constexpr int C = 32 * E;
     unsigned mask = __ballot_sync(0xffffffffu, st.cnt > C - 8);
@@ -126,7 +129,7 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
         uint64_t key[E];
         const uint64_t kth = warp_compact<E>(b, k, key);
         if (static_cast<int>(lane) == l) {
-            st.thr = publish_and_refresh(st.gq, kth, st.thr);
+            st.thr = publish_and_refresh<strict_own>(st.gq, kth, st.thr);
             st.cnt = st.cnt < k ? st.cnt : k;
         }
     }
@@ -425,7 +428,8 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
-        if constexpr (E > 0) make_room<E>(st, k);
+        // rows of a list are stored in no particular id order: equal scores must stay candidates (keys decide)
+        if constexpr (E > 0) make_room<E, false>(st, k);
 #pragma unroll
         for (int j = 8 * g; j < 8 * g + 8; ++j) {
             const float s = __uint_as_float(v[j]);
@@ -438,7 +442,7 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
                     // top-1: ids are not visited in increasing order here, so ties go through the key
                     const uint64_t key = make_key(s, id);
                     if (key > st.best) st.best = key;
-                    st.thr = key_score(st.best);
+                    st.thr = thr_from_shared(static_cast<uint32_t>(st.best >> 32));  // equal scores still pass
                 }
             }
         }
@@ -494,12 +498,13 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int n_items = __ldg(p.n_items_ptr);
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const GroupItem it = p.items[w];
             const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
             for (int t = 0; t < n_tiles; ++t) {
@@ -523,7 +528,7 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const GroupItem it = p.items[w];
             const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
             for (int t = 0; t < n_tiles; ++t) {
@@ -558,7 +563,7 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         LaneTopk<E> st;
         uint64_t* warp_buf = p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C;
         if constexpr (E > 0) st.buf = warp_buf + static_cast<size_t>(lane) * C;
-        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const GroupItem it = p.items[w];
             const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
             const int a_local = ewarp * 32 + static_cast<int>(lane);

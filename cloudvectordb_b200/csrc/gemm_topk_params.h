@@ -38,7 +38,7 @@ struct GroupItem {
 };
 
 struct GroupedParams {
-    int n_items;
+    const int* n_items_ptr;  // device scalar: number of work items (written by the bucketing kernels)
     int k;
     int nkb, k16;
     const GroupItem* items;

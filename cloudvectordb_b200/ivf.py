@@ -5,10 +5,10 @@ assignment, and an nprobe search that scans only the probed lists.
 FAISS ``IndexIVFFlat`` shape: ``train(x)``, ``add(x)``, ``search(q, k)`` with the
 ``nprobe`` attribute, ``ntotal``, ``nlist``.  Everything numeric runs in the CUDA
 library: the coarse search and the assignment are the fused GEMM + top-k kernel
-over the centroids, the list scan is its grouped variant (one work item per
-probed list and up to 128 of the queries probing it).  torch is used for device
-buffers and for ordering the rows by list at build time (a stable sort of the
-assignment vector).
+over the centroids, the rows are bucketed into lists by histogram / scan /
+scatter kernels, and the list scan is the grouped variant of the fused kernel
+(one work item per probed list and up to 128 of the queries probing it).
+torch only provides the device buffers.
 """
 from __future__ import annotations
 
@@ -30,8 +30,7 @@ class IndexIVFFlat:
         self.quantizer = IndexFlat(d, self.metric, "bf16", device)   # the centroids
         self.lists = IndexFlat(d, self.metric, "bf16", device)       # the rows, stored list-major once grouped
         self.centroids: Optional[torch.Tensor] = None
-        self._assign = torch.empty((0,), dtype=torch.int32, device=self._dev())  # list of every stored row
-        self._ids = torch.empty((0,), dtype=torch.int32, device=self._dev())     # caller id of every stored row
+        self._assign = torch.empty((0,), dtype=torch.int32, device=self._dev())  # list of every row, by row id
         self._grouped = False
         self.list_offsets: Optional[torch.Tensor] = None
 
@@ -76,25 +75,17 @@ class IndexIVFFlat:
             raise RuntimeError("train() first")
         x = self._to_device(x)
         a = self.assign_lists(x)
-        base = int(self.ntotal)
         self.lists.add(x)                # add() un-groups the stored rows (new rows are appended in insertion order)
         self._assign = torch.cat([self._assign, a])
-        self._ids = torch.cat([self._ids, torch.arange(base, base + x.shape[0], dtype=torch.int32, device=self._dev())])
         self._grouped = False
 
     def _group(self) -> None:
-        """Store the rows list-major (stable: ids ascend inside a list)."""
-        order = torch.sort(self._assign.long(), stable=True).indices
-        perm = order.to(torch.int32).contiguous()
-        self._ids = self._ids[order].contiguous()
-        self._assign = self._assign[order].contiguous()
-        counts = torch.bincount(self._assign.long(), minlength=self.nlist)
-        off = torch.zeros((self.nlist + 1,), dtype=torch.int64, device=self._dev())
-        off[1:] = torch.cumsum(counts, 0)
-        self.list_offsets = off.to(torch.int32).contiguous()
+        """Store the rows list-major (histogram / scan / scatter kernels in the library)."""
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
-        _C.check(_C.lib().cvdb_index_group_rows(self.lists._h, perm.data_ptr(), self._ids.data_ptr(),
-                                                self.list_offsets.data_ptr(), self.nlist, stream))
+        self._assign = self._assign.contiguous()
+        _C.check(_C.lib().cvdb_index_group_by_list(self.lists._h, self._assign.data_ptr(), self.nlist, stream))
+        self.list_offsets = torch.empty((self.nlist + 1,), dtype=torch.int32, device=self._dev())
+        _C.check(_C.lib().cvdb_index_list_offsets(self.lists._h, self.list_offsets.data_ptr(), stream))
         self._grouped = True
 
     # ----------------------------------------------------------------- search
@@ -126,10 +117,8 @@ class IndexIVFFlat:
         return D, I
 
     def list_of_row(self) -> torch.Tensor:
-        """List id of every row, indexed by caller id (int32, on the GPU)."""
-        out = torch.empty_like(self._assign)
-        out[self._ids.long()] = self._assign
-        return out
+        """List id of every row, indexed by row id (int32, on the GPU)."""
+        return self._assign
 
     def close(self) -> None:
         self.quantizer.close()

@@ -109,14 +109,15 @@ int cvdb_index_last_work(cvdb_index_t idx, double* flops, double* db_bytes, int*
 int cvdb_index_last_variant(cvdb_index_t idx);
 
 /* -- inverted lists (IVF) on top of the coarse quantizer -------------------------
- * cvdb_index_group_rows re-stores the rows list-major: stored position p receives the row that is currently at
- * position perm[p]; row_ids[p] is the caller-visible id reported for position p; list_offsets [nlist+1] are the
- * list boundaries in stored positions.  All three are DEVICE pointers (int32).  bf16 storage only.  add() after
- * grouping un-groups the index (the caller re-groups).
+ * cvdb_index_group_by_list re-stores the rows list-major.  list_of_id [ntotal] (int32, DEVICE pointer) names the
+ * list (0..nlist-1) of every row, indexed by row id (= insertion order).  Rows added after an earlier grouping are
+ * picked up by calling it again with the complete vector.  bf16 storage only.  The order of rows inside a list is
+ * unspecified; results do not depend on it (candidates carry their row id).  add() un-groups the index.
+ * cvdb_index_list_offsets copies the nlist+1 list boundaries (stored positions) to a DEVICE buffer.
  * cvdb_index_search_lists: like cvdb_index_search, but query i only scans the lists probes[i][0..nprobe)
- * (int32, follows on_device; entries < 0 are skipped).  Returned ids are row_ids values. */
-int cvdb_index_group_rows(cvdb_index_t idx, const int32_t* perm, const int32_t* row_ids, const int32_t* list_offsets,
-                          int nlist, void* stream);
+ * (int32, follows on_device; entries < 0 are skipped).  Returned ids are row ids. */
+int cvdb_index_group_by_list(cvdb_index_t idx, const int32_t* list_of_id, int nlist, void* stream);
+int cvdb_index_list_offsets(cvdb_index_t idx, int32_t* out_device, void* stream);
 int cvdb_index_search_lists(cvdb_index_t idx, const void* q, int64_t nq, int dtype, int k, const int32_t* probes,
                             int nprobe, float* D, int64_t* I, int on_device, void* stream);
 

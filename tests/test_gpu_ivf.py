@@ -111,3 +111,43 @@ def test_ivf_empty_lists_and_padding():
     assert np.array_equal(I, I_ref)
     assert np.all(np.isneginf(D[I < 0]))
     ivf.close()
+
+
+def test_ivf_add_after_search_regroups():
+    """Rows added after a first search are picked up: the lists are rebuilt, ids stay insertion order."""
+    from cloudvectordb_b200 import IndexIVFFlat
+    rng = np.random.default_rng(13)
+    n, d, nlist, nq, k, nprobe = 9000, 48, 32, 120, 10, 6
+    xb = O.bf16_round(unit_rows(rng, n, d))
+    xq = O.bf16_round(unit_rows(rng, nq, d))
+    cent = O.bf16_round(xb[rng.choice(n, nlist, replace=False)])
+    ivf = IndexIVFFlat(d, nlist, "ip", device=0)
+    ivf.train(None, centroids=cent)
+    for lo, hi in ((0, 4000), (4000, 4001), (4001, 9000)):
+        ivf.add(xb[lo:hi])
+        D, I = ivf.search(xq, k, nprobe=nprobe)          # groups (again) on demand
+        a = ivf.list_of_row().cpu().numpy()
+        assert a.shape[0] == hi and int(ivf.list_offsets[-1]) == hi
+        probes = ivf.probe(xq, nprobe).cpu().numpy()
+        D_ref, I_ref = O.ivf_search_ref(xb[:hi], a, xq, k, probes, O.METRIC_IP)
+        assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
+        assert I.max() < hi
+    ivf.close()
+
+
+def test_ivf_duplicate_rows_tie_by_row_id():
+    """Equal scores inside and across lists come back in row-id order although rows are stored unordered."""
+    from cloudvectordb_b200 import IndexIVFFlat
+    rng = np.random.default_rng(17)
+    d, nlist = 32, 4
+    cent = O.bf16_round(unit_rows(rng, nlist, d))
+    base = O.bf16_round(unit_rows(rng, 40, d))
+    xb = np.concatenate([base, base, base])              # every row three times: ids i, i+40, i+80
+    ivf = IndexIVFFlat(d, nlist, "ip", device=0)
+    ivf.train(None, centroids=cent)
+    ivf.add(xb)
+    D, I = ivf.search(base, 3, nprobe=nlist)
+    assert np.array_equal(I, np.stack([np.arange(40), np.arange(40) + 40, np.arange(40) + 80], 1))
+    D1, I1 = ivf.search(base, 1, nprobe=nlist)           # top-1 path
+    assert np.array_equal(I1[:, 0], np.arange(40))
+    ivf.close()
