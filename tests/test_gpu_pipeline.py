@@ -85,3 +85,15 @@ def test_streaming_add_from_file(tmp_path):
     with pytest.raises(ValueError):
         idx.add_from_file(bad)
     idx.close()
+
+
+def test_example_pipeline_runs(tmp_path, capsys):
+    """examples/build_vectordb.py: mining -> triplets -> save/load -> IVF on a small synthetic corpus."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("build_vectordb", os.path.join(root, "examples", "build_vectordb.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(["--rows", "20000", "--dim", "64", "--nlist", "64", "--out", str(tmp_path / "c.cvdb")]) == 0
+    out = capsys.readouterr().out
+    assert "PIPELINE_OK" in out and "triplets" in out
