@@ -42,7 +42,9 @@ def main(argv=None):
         emb = None
     else:
         g = torch.Generator(device=dev).manual_seed(0)
-        docs = torch.randn((a.rows // a.group_size + 1, a.dim), generator=g, device=dev)
+        topics = torch.randn((256, a.dim), generator=g, device=dev)
+        n_docs = a.rows // a.group_size + 1
+        docs = topics[torch.randint(0, 256, (n_docs,), generator=g, device=dev)] + 0.5 * torch.randn((n_docs, a.dim), generator=g, device=dev)
         emb = docs.repeat_interleave(a.group_size, 0)[: a.rows] + 0.4 * torch.randn((a.rows, a.dim), generator=g, device=dev)
         emb = torch.nn.functional.normalize(emb, dim=1).bfloat16()
         flat.add(emb)
