@@ -2,6 +2,7 @@
 // padded bf16 planes, norms), the k-way merges, and the k-means update.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -24,6 +25,7 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 
 // ---------------------------------------------------------------------------
 // pack_rows: one warp per row.

@@ -211,6 +211,8 @@ int pack_dispatch(const void* in, int dtype, int64_t n, __nv_bfloat16* out, cons
     if (n == 0) return CVDB_OK;
     if (dtype == CVDB_DTYPE_F32)
         launch_pack<float>(static_cast<const float*>(in), n, ix->d, out, ix, is_query, norms, st);
+    else if (dtype == CVDB_DTYPE_F16)
+        launch_pack<__half>(static_cast<const __half*>(in), n, ix->d, out, ix, is_query, norms, st);
     else
         launch_pack<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(in), n, ix->d, out, ix, is_query, norms, st);
     CU_TRY(cudaGetLastError());
@@ -613,12 +615,13 @@ int cvdb_index_add(cvdb_index_t h, const void* x, int64_t n, int dtype, int on_d
     if (n < 0) return fail(CVDB_EINVAL, "n < 0");
     if (n == 0) return CVDB_OK;
     if (!x) return fail(CVDB_EINVAL, "x is null");
-    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
     if (ix->ntotal + n > 0x7FFFFF00LL) return fail(CVDB_ELIMIT, "an index holds fewer than 2^31 rows per GPU");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TRY(grow(ix, ix->ntotal + n, st));
-    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     __nv_bfloat16* dst = ix->x + ix->ntotal * ix->row_elems;
     if (on_device) {
         TRY(pack_dispatch(x, dtype, n, dst, ix, 0, nullptr, st));
@@ -663,7 +666,8 @@ int cvdb_index_search(cvdb_index_t h, const void* q, int64_t nq, int dtype, int 
     Index* ix = reinterpret_cast<Index*>(h);
     if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
     if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
-    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
     if (nq == 0) return CVDB_OK;
     if (!q || !D || !I) return fail(CVDB_EINVAL, "q, D and I must be non-null");
     if (opts && opts->group_q && !ix->has_groups)
@@ -672,7 +676,7 @@ int cvdb_index_search(cvdb_index_t h, const void* q, int64_t nq, int dtype, int 
         return fail(CVDB_EINVAL, "rows are stored list-major (cvdb_index_group_by_list): use cvdb_index_search_lists");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     const int64_t chunk = query_chunk(ix, k);
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
         const int64_t m = std::min(chunk, nq - q0);
@@ -715,12 +719,13 @@ int cvdb_index_assign(cvdb_index_t h, const void* x, int64_t n, int dtype, int32
     TRY(check_index(h));
     Index* ix = reinterpret_cast<Index*>(h);
     if (n < 0) return fail(CVDB_EINVAL, "n < 0");
-    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
     if (n == 0) return CVDB_OK;
     if (!x || !assign) return fail(CVDB_EINVAL, "x and assign must be non-null");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     const int64_t chunk = query_chunk(ix, 1);
     for (int64_t q0 = 0; q0 < n; q0 += chunk) {
         const int64_t m = std::min(chunk, n - q0);
@@ -870,12 +875,13 @@ int cvdb_index_search_lists(cvdb_index_t h, const void* q, int64_t nq, int dtype
     if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
     if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
     if (nprobe < 1 || nprobe > 4096) return fail(CVDB_ELIMIT, "nprobe=%d outside [1, 4096]", nprobe);
-    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16) return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
     if (nq == 0) return CVDB_OK;
     if (!q || !probes || !D || !I) return fail(CVDB_EINVAL, "q, probes, D and I must be non-null");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     // bound the gathered-query scratch: at most 2^18 (query, probe) pairs per launch
     const int64_t chunk = std::max<int64_t>(1, (int64_t(1) << 18) / nprobe);
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -1007,6 +1013,9 @@ int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int
     else if (dtype == CVDB_DTYPE_BF16)
         kmeans_update_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(x), n, d, assign, sums, counts);
+    else if (dtype == CVDB_DTYPE_F16)
+        kmeans_update_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const __half*>(x), n, d,
+                                                                                    assign, sums, counts);
     else
         return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
     ++g_launches;

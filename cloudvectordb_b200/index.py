@@ -43,8 +43,10 @@ class _Buf:
                 self.dtype = _C.DTYPE_F32
             elif x.dtype == torch.bfloat16:
                 self.dtype = _C.DTYPE_BF16
+            elif x.dtype == torch.float16:
+                self.dtype = _C.DTYPE_F16
             else:
-                raise TypeError(f"{what}: dtype {x.dtype} not supported (float32 or bfloat16)")
+                raise TypeError(f"{what}: dtype {x.dtype} not supported (float32, bfloat16 or float16)")
             x = x.contiguous()
             self.on_device = x.is_cuda
             self.device_index = x.device.index if x.is_cuda else None
@@ -56,10 +58,13 @@ class _Buf:
                 x = x.reshape(1, -1)
             if x.ndim != 2:
                 raise ValueError(f"{what} must be 2-D [n, d]")
-            if x.dtype != np.float32:
-                x = x.astype(np.float32)
+            if x.dtype == np.float16:
+                self.dtype = _C.DTYPE_F16
+            else:
+                if x.dtype != np.float32:
+                    x = x.astype(np.float32)
+                self.dtype = _C.DTYPE_F32
             x = np.ascontiguousarray(x)
-            self.dtype = _C.DTYPE_F32
             self.on_device = False
             self.device_index = None
             self.ptr = x.ctypes.data
@@ -242,7 +247,7 @@ class IndexFlat:
     def add_from_file(self, path: str, dtype: str = "float32", chunk_rows: int = 1 << 18, offset: int = 0) -> int:
         """Streaming add() of a raw row-major [n, d] matrix on disk (float32 or bfloat16), memory-mapped
         and fed in chunks so the corpus never has to be resident on the host.  Returns the rows added."""
-        esz = {"float32": 4, "bfloat16": 2}[dtype]
+        esz = {"float32": 4, "bfloat16": 2, "float16": 2}[dtype]
         size = os.path.getsize(path) - offset
         if size % (esz * self._d):
             raise ValueError("file size is not a whole number of rows")
@@ -250,7 +255,7 @@ class IndexFlat:
         mm = np.memmap(path, dtype=np.float32 if esz == 4 else np.uint16, mode="r", offset=offset, shape=(n, self._d))
         for r0 in range(0, n, chunk_rows):
             blk = np.ascontiguousarray(mm[r0:r0 + chunk_rows])
-            code = _C.DTYPE_F32 if esz == 4 else _C.DTYPE_BF16
+            code = {"float32": _C.DTYPE_F32, "bfloat16": _C.DTYPE_BF16, "float16": _C.DTYPE_F16}[dtype]
             _C.check(_C.lib().cvdb_index_add(self._h, blk.ctypes.data, blk.shape[0], code, 0, None))
         return int(n)
 

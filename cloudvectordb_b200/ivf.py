@@ -40,7 +40,7 @@ class IndexIVFFlat:
     def _to_device(self, x):
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        if x.dtype not in (torch.float32, torch.bfloat16):
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             x = x.float()
         return x.to(self._dev()).contiguous()
 

@@ -35,7 +35,7 @@ class Kmeans:
     def _to_device(self, x):
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        if x.dtype not in (torch.float32, torch.bfloat16):
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             x = x.float()
         return x.to(self._dev()).contiguous()
 
@@ -69,7 +69,7 @@ class Kmeans:
         sums = torch.zeros((self.k, self.d), dtype=torch.float32, device=x.device)
         counts = torch.zeros((self.k,), dtype=torch.int32, device=x.device)
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
-        dt = _C.DTYPE_F32 if x.dtype == torch.float32 else _C.DTYPE_BF16
+        dt = {torch.float32: _C.DTYPE_F32, torch.bfloat16: _C.DTYPE_BF16, torch.float16: _C.DTYPE_F16}[x.dtype]
         _C.check(lib.cvdb_kmeans_accumulate(x.data_ptr(), x.shape[0], self.d, dt, assign.data_ptr(), sums.data_ptr(),
                                             counts.data_ptr(), stream))
         obj = dist_sq.double().sum()

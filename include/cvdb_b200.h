@@ -47,6 +47,7 @@ extern "C" {
 
 #define CVDB_DTYPE_F32 0
 #define CVDB_DTYPE_BF16 1
+#define CVDB_DTYPE_F16 2 /* input only: rows and queries are converted to the index storage on the way in */
 
 /* how database rows are kept in HBM */
 #define CVDB_STORE_BF16 0  /* one bf16 plane: bf16 x bf16 -> fp32 tensor-core scores */

@@ -424,6 +424,32 @@ def test_large_database_properties():
     assert torch.equal(Im, I) and torch.equal(Dm, D)
 
 
+def test_fp16_inputs():
+    """float16 rows / queries (numpy or torch, host or device) are converted on the way in."""
+    rng = np.random.default_rng(92)
+    n, d, nq, k = 4000, 72, 90, 10
+    xb16 = unit_rows(rng, n, d).astype(np.float16)
+    xq16 = unit_rows(rng, nq, d).astype(np.float16)
+    # what the engine stores: fp16 value rounded to bf16
+    xb, xq = O.bf16_round(xb16.astype(np.float32)), O.bf16_round(xq16.astype(np.float32))
+    for metric in ("ip", "l2"):
+        D_ref, I_ref = O.search_ref(xb, xq, k, M[metric])
+        idx = make_index(d, metric, "bf16")
+        idx.add(xb16[:1500])                                        # numpy fp16, host
+        idx.add(torch.from_numpy(xb16[1500:]).cuda())               # torch fp16, device
+        D, I = idx.search(xq16, k)
+        assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5)
+        D, I = idx.search(torch.from_numpy(xq16).cuda(), k)
+        assert_parity(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, metric, tie_tol=2e-5)
+        idx.close()
+    ex = make_index(d, "ip", "exact")                               # exact storage keeps the fp16 values exactly
+    ex.add(xb16)
+    D, I = ex.search(xq16, k)
+    ex.close()
+    D_ref, I_ref = O.search_ref(xb16.astype(np.float32), xq16.astype(np.float32), k, O.METRIC_IP)
+    assert_parity(D, I, D_ref, I_ref, "ip", tie_tol=1e-5, dtol=1e-5)
+
+
 def test_query_batches_larger_than_one_launch_are_chunked():
     """More than 65 536 queries (262 144 for k = 1) go through several launches inside one call."""
     rng = np.random.default_rng(91)

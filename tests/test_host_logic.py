@@ -42,6 +42,7 @@ def test_header_constants_match_binding():
     consts = dict(re.findall(r"#define\s+(CVDB_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", txt))
     assert int(consts["CVDB_METRIC_L2"]) == _C.METRIC_L2
     assert int(consts["CVDB_DTYPE_BF16"]) == _C.DTYPE_BF16
+    assert int(consts["CVDB_DTYPE_F16"]) == _C.DTYPE_F16
     assert int(consts["CVDB_STORE_EXACT"]) == _C.STORE_EXACT
     assert int(consts["CVDB_MAX_K"]) == _C.MAX_K
     assert int(consts["CVDB_ECUDA"]) == _C.ECUDA

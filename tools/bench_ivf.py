@@ -99,6 +99,21 @@ def main():
         ms = float(np.median(ts))
         emit(event="search", nprobe=nprobe, ms_per_batch=ms, qps=a.nq / ms * 1e3, recall_at_k_vs_exact=hit,
              speedup_vs_flat=t_flat / ms, items=ivf.lists.last_work()["grid"])
+    # small batches: end-to-end latency of one search call (coarse search + bucketing + list scan + merge)
+    for nq in (1, 16, 64, 256):
+        q = xq[:nq]
+        for nprobe in (8, 32):
+            lat = []
+            for it in range(30):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                D, I = ivf.search(q, a.k, nprobe=nprobe)
+                torch.cuda.synchronize()
+                if it >= 5:
+                    lat.append((time.perf_counter() - t0) * 1e3)
+            hit = (I[:, :, None] == I_ex[:nq, None, :]).any(-1).float().sum(1).mean().item() / a.k
+            emit(event="small_batch", nq=nq, nprobe=nprobe, latency_ms_p50=float(np.percentile(lat, 50)),
+                 latency_ms_p99=float(np.percentile(lat, 99)), recall_at_k_vs_exact=hit)
     ivf.close()
 
 
