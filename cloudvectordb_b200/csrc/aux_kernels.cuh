@@ -88,40 +88,55 @@ __global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, i
 }
 
 // ---------------------------------------------------------------------------
-// merge_partials: final k-way select over the per-slice lists of one query
-// (one warp per query), turn keys into (D, I).
+// merge_partials: final k-way merge of the per-slice (or per-probe) lists of one
+// query, one warp per query, keys -> (D, I).
 //   IP: D = score.            L2: D = |q|^2 - 2*score (squared distance).
 //   Missing results: I = -1, D = -inf (IP) / +inf (L2).
-// Keys are unique (distinct rows), so "largest key below the previous pick"
-// enumerates the candidates in order.
+// Every list is sorted descending with its empty slots (key 0) at the end, so
+// this is a head-pointer merge: lane l owns lists l, l+32, ...; per output rank
+// each lane offers the best head among its lists, the warp picks the largest
+// and the owning lane advances that head.  Cost per query: k * n_lists / 32
+// loads per lane (the old "rescan everything per rank" cost k * n_lists * k / 32).
+// Dynamic shared memory: blockDim.x/32 * n_lists uint16 head positions.
 // ---------------------------------------------------------------------------
 template <typename Tidx>
-__global__ void merge_partials_kernel(const uint64_t* __restrict__ part, int64_t nq, int n_cand, int k, int l2,
+__global__ void merge_partials_kernel(const uint64_t* __restrict__ part, int64_t nq, int n_lists, int k_in, int k, int l2,
                                       const float* __restrict__ qnorm, int64_t id_base, float* __restrict__ D,
                                       Tidx* __restrict__ I) {
+    extern __shared__ uint16_t s_heads[];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
-    const uint64_t* c = part + q * n_cand;
-    uint64_t prev = ~0ull;
+    uint16_t* head = s_heads + static_cast<size_t>(wib) * n_lists;
+    for (int l = lane; l < n_lists; l += 32) head[l] = 0;
+    __syncwarp();
+    const uint64_t* c = part + q * static_cast<int64_t>(n_lists) * k_in;
     for (int r = 0; r < k; ++r) {
         uint64_t best = 0;
-        for (int i = lane; i < n_cand; i += 32) {
-            const uint64_t key = c[i];
-            if (key < prev && key > best) best = key;
-        }
-        best = warp_max_u64(best);
-        if (lane == 0) {
-            if (best == 0) {
-                D[q * k + r] = l2 ? INFINITY : -INFINITY;
-                I[q * k + r] = static_cast<Tidx>(-1);
-            } else {
-                const float s = key_score(best);
-                D[q * k + r] = l2 ? (qnorm[q] - 2.f * s) : s;
-                I[q * k + r] = static_cast<Tidx>(static_cast<int64_t>(key_row(best)) + id_base);
+        int bl = -1;
+        for (int l = lane; l < n_lists; l += 32) {
+            const int h = head[l];
+            if (h < k_in) {
+                const uint64_t key = c[static_cast<int64_t>(l) * k_in + h];
+                if (key > best) { best = key; bl = l; }
             }
         }
-        prev = best ? best : 0;
+        const uint64_t win = warp_max_u64(best);
+        if (win == 0) {  // every list is exhausted: pad the rest
+            for (int rr = r + lane; rr < k; rr += 32) {
+                D[q * k + rr] = l2 ? INFINITY : -INFINITY;
+                I[q * k + rr] = static_cast<Tidx>(-1);
+            }
+            break;
+        }
+        if (best == win) {  // keys are unique (distinct rows): exactly one lane holds the winner
+            head[bl] = static_cast<uint16_t>(head[bl] + 1);
+            const float s = key_score(win);
+            D[q * k + r] = l2 ? (qnorm[q] - 2.f * s) : s;
+            I[q * k + r] = static_cast<Tidx>(static_cast<int64_t>(key_row(win)) + id_base);
+        }
+        __syncwarp();
     }
 }
 

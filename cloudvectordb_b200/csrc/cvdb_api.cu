@@ -286,11 +286,11 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         CU_TRY(cudaMemsetAsync(ix->part.p, 0, static_cast<size_t>(nq) * k * 8, st));
         const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
         if (I64)
-            merge_partials_kernel<int64_t><<<blocks, 256, 0, st>>>(ix->part.as<uint64_t>(), nq, k, k, l2,
-                                                                   ix->q_norm.as<float>(), id_base, D, I64);
+            merge_partials_kernel<int64_t><<<blocks, 256, 8 * sizeof(uint16_t), st>>>(
+                ix->part.as<uint64_t>(), nq, 1, k, k, l2, ix->q_norm.as<float>(), id_base, D, I64);
         else
-            merge_partials_kernel<int32_t><<<blocks, 256, 0, st>>>(ix->part.as<uint64_t>(), nq, k, k, l2,
-                                                                   ix->q_norm.as<float>(), id_base, D, I32);
+            merge_partials_kernel<int32_t><<<blocks, 256, 8 * sizeof(uint16_t), st>>>(
+                ix->part.as<uint64_t>(), nq, 1, k, k, l2, ix->q_norm.as<float>(), id_base, D, I32);
         ++g_launches;
         CU_TRY(cudaGetLastError());
         return CVDB_OK;
@@ -403,11 +403,11 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
 
     const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
     if (I64)
-        merge_partials_kernel<int64_t><<<blocks, 256, 0, st>>>(p.part, nq, p.n_slices * k, k, l2, ix->q_norm.as<float>(),
-                                                               id_base, D, I64);
+        merge_partials_kernel<int64_t><<<blocks, 256, 8 * p.n_slices * sizeof(uint16_t), st>>>(
+            p.part, nq, p.n_slices, k, k, l2, ix->q_norm.as<float>(), id_base, D, I64);
     else
-        merge_partials_kernel<int32_t><<<blocks, 256, 0, st>>>(p.part, nq, p.n_slices * k, k, l2, ix->q_norm.as<float>(),
-                                                               id_base, D, I32);
+        merge_partials_kernel<int32_t><<<blocks, 256, 8 * p.n_slices * sizeof(uint16_t), st>>>(
+            p.part, nq, p.n_slices, k, k, l2, ix->q_norm.as<float>(), id_base, D, I32);
     ++g_launches;
     CU_TRY(cudaGetLastError());
 
@@ -503,8 +503,8 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
     ix->last_grid = n_items;
     ix->last_variant = 5;
     const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
-    merge_partials_kernel<int64_t><<<blocks, 256, 0, st>>>(ix->part.as<uint64_t>(), nq, nprobe * k, k, l2,
-                                                           ix->q_norm.as<float>(), 0, D, I);
+    merge_partials_kernel<int64_t><<<blocks, 256, 8 * nprobe * sizeof(uint16_t), st>>>(
+        ix->part.as<uint64_t>(), nq, nprobe, k, k, l2, ix->q_norm.as<float>(), 0, D, I);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return CVDB_OK;
@@ -874,7 +874,7 @@ int cvdb_index_search_lists(cvdb_index_t h, const void* q, int64_t nq, int dtype
     if (!ix->grouped) return fail(CVDB_EINVAL, "rows are not grouped into lists (cvdb_index_group_by_list)");
     if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
     if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
-    if (nprobe < 1 || nprobe > 4096) return fail(CVDB_ELIMIT, "nprobe=%d outside [1, 4096]", nprobe);
+    if (nprobe < 1 || nprobe > 2048) return fail(CVDB_ELIMIT, "nprobe=%d outside [1, 2048]", nprobe);
     if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
         return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
     if (nq == 0) return CVDB_OK;
