@@ -52,9 +52,19 @@ def parse():
     return ap.parse_args()
 
 
+METRIC = "queries/sec at 10M x 768 k=10"   # BASELINE.json "metric"
+
+
 def workload_name(a):
     return (f"exact top-{a.k} {a.metric.upper()} search, {a.rows}x{a.dim} bf16 database, "
             f"{a.nq}-query batches (BASELINE.json configs[1])")
+
+
+def workload_config(a, world):
+    return {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "queries_per_step": a.nq,
+            "k": a.k, "metric": a.metric, "distribution": "iid unit-norm Gaussian rows, seeds 1234/5678",
+            "sharding": f"rows split over {world} rank(s), one all-gather of (D,I) + k-way select",
+            "cache": "inputs larger than L2 (database 15.4 GB vs 126 MB L2), no explicit flush"}
 
 
 def load_peaks():
@@ -100,11 +110,11 @@ def run_reference(a):
         return
     base, t = cpu_sample_qps(a, max(1, a.steps), max(0, a.warmup))
     out = {
-        "impl": "reference", "metric": "queries/sec", "value": base["value"], "unit": "queries/s",
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "reference ships no code (README.md only): the CPU arm is the "
-                   "NumPy IndexFlat oracle port on a bounded sample"},
+        "config": dict(workload_config(a, max(1, a.gpus)), note="reference ships no code (README.md only): the CPU arm is "
+                       "the NumPy IndexFlat oracle port on a bounded sample of this workload"),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -341,13 +351,10 @@ def run_ours(a):
 
     if rank == 0:
         out = {
-            "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "queries_per_step": a.nq,
-                       "k": a.k, "metric": a.metric, "distribution": "iid unit-norm Gaussian rows, seeds 1234/5678",
-                       "sharding": f"rows split over {world} rank(s), one all-gather of (D,I) + k-way select",
-                       "cache": "inputs larger than L2 (database 15.4 GB vs 126 MB L2), no explicit flush"},
+            "config": workload_config(a, world),
             "e2e": {"value": a.nq / e2e_ms * 1e3, "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "same_ids_as_device_path": same_e2e},
             "gpu_launches": int(launches),

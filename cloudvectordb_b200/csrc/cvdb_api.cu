@@ -222,6 +222,9 @@ int pack_dispatch(const void* in, int dtype, int64_t n, __nv_bfloat16* out, cons
 // ------------------------------------------------------- kernel selection
 constexpr int kBlockN = 256;
 
+// Candidate-buffer size (32*E slots per query): about twice k, so that a compaction (a bitonic sort of the whole
+// buffer) is needed only once per ~k accepted rows.  k in (248, 504] has to make do with 512 slots: it works but
+// compacts more and more often as k approaches 504 (known gaps).
 int pick_E(int k) {
     if (k == 1) return 0;
     if (k <= 12) return 1;
