@@ -16,7 +16,7 @@ OK, EINVAL, ECUDA, ENOMEM, ELIMIT = 0, -1, -2, -3, -4
 METRIC_IP, METRIC_L2 = 0, 1
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 STORE_BF16, STORE_EXACT = 0, 1
-MAX_K = 504
+MAX_K = 2048
 
 
 class CvdbError(RuntimeError):

@@ -223,15 +223,18 @@ int pack_dispatch(const void* in, int dtype, int64_t n, __nv_bfloat16* out, cons
 constexpr int kBlockN = 256;
 
 // Candidate-buffer size (32*E slots per query): about twice k, so that a compaction (a bitonic sort of the whole
-// buffer) is needed only once per ~k accepted rows.  k in (248, 504] has to make do with 512 slots: it works but
-// compacts more and more often as k approaches 504 (known gaps).
+// buffer) is needed only once per ~k accepted rows.  Up to 512 slots the sort runs in registers; larger buffers
+// (k > 248) are sorted in place in L2-resident memory.
 int pick_E(int k) {
     if (k == 1) return 0;
     if (k <= 12) return 1;
     if (k <= 28) return 2;
     if (k <= 60) return 4;
     if (k <= 124) return 8;
-    return 16;
+    if (k <= 248) return 16;
+    if (k <= 504) return 32;
+    if (k <= 1016) return 64;
+    return 128;
 }
 
 // Split the database into slices so that (query tiles x slices) fills the grid

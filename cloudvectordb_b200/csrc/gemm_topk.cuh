@@ -115,6 +115,37 @@ __device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&
     return warp_sorted_at<E>(key, k - 1);
 }
 
+// Large buffers (E > 16, i.e. k > 248): the same bitonic network, but run as loops over the buffer where it
+// lives (L2-resident global memory) instead of unrolled over registers -- a 1024..4096-key register network would
+// not fit the register file (and takes minutes to compile).  Slower per sort, but these buffers are sized >= 2k so
+// sorts are rare.  Returns the k-th best key; leaves the best k sorted at the front and zeros behind them.
+template <int E>
+__device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k) {
+    constexpr int C = 32 * E;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int size = 2; size <= C; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int sh = __ffs(stride) - 1;
+            for (int t = lane; t < C / 2; t += 32) {
+                const int i = ((t >> sh) << (sh + 1)) | (t & (stride - 1));
+                const int j = i + stride;
+                const bool desc = (size == C) || ((i & size) == 0);
+                const uint64_t a = __ldcg(reinterpret_cast<const unsigned long long*>(b + i));
+                const uint64_t c = __ldcg(reinterpret_cast<const unsigned long long*>(b + j));
+                if (desc ? (a < c) : (a > c)) {
+                    b[i] = c;
+                    b[j] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (int p = k + lane; p < C; p += 32) b[p] = 0;
+    __syncwarp();
+    return __ldcg(reinterpret_cast<const unsigned long long*>(b + k - 1));
+}
+
 template <int E, bool strict_own = true>
 __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
     constexpr int C = 32 * E;
@@ -126,8 +157,13 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
         const int l = __ffs(mask) - 1;
         mask &= mask - 1;
         uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
-        uint64_t key[E];
-        const uint64_t kth = warp_compact<E>(b, k, key);
+        uint64_t kth;
+        if constexpr (E <= 16) {
+            uint64_t key[E];
+            kth = warp_compact<E>(b, k, key);
+        } else {
+            kth = warp_compact_mem<E>(b, k);
+        }
         if (static_cast<int>(lane) == l) {
             st.thr = publish_and_refresh<strict_own>(st.gq, kth, st.thr);
             st.cnt = st.cnt < k ? st.cnt : k;
@@ -204,15 +240,22 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
             const int qr = q_base + l;
             if (qr >= p.nq) break;
             uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
-            uint64_t key[E];
-            const uint64_t kth = warp_compact<E>(b, p.k, key);
-            if (static_cast<int>(lane) == l && kth != 0 && st.gq != nullptr) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
             uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
+            uint64_t kth;
+            if constexpr (E <= 16) {
+                uint64_t key[E];
+                kth = warp_compact<E>(b, p.k, key);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int pos = e * 32 + lane;
-                if (pos < p.k) out[pos] = key[e];
+                for (int e = 0; e < E; ++e) {
+                    const int pos = e * 32 + lane;
+                    if (pos < p.k) out[pos] = key[e];
+                }
+            } else {
+                kth = warp_compact_mem<E>(b, p.k);
+                for (int pos = lane; pos < p.k; pos += 32)
+                    out[pos] = __ldcg(reinterpret_cast<const unsigned long long*>(b + pos));
             }
+            if (static_cast<int>(lane) == l && kth != 0 && st.gq != nullptr) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
         }
         __syncwarp();
     } else {
@@ -608,15 +651,22 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     const int dst_l = __shfl_sync(0xffffffffu, dst, l);
                     if (dst_l < 0) continue;  // warp-uniform
                     uint64_t* b = warp_buf + static_cast<size_t>(l) * C;
-                    uint64_t key[E];
-                    const uint64_t kth = warp_compact<E>(b, p.k, key);
-                    if (static_cast<int>(lane) == l && kth != 0) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
                     uint64_t* out = p.part + static_cast<size_t>(dst_l) * p.k;
+                    uint64_t kth;
+                    if constexpr (E <= 16) {
+                        uint64_t key[E];
+                        kth = warp_compact<E>(b, p.k, key);
 #pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int pos = e * 32 + lane;
-                        if (pos < p.k) out[pos] = key[e];
+                        for (int e = 0; e < E; ++e) {
+                            const int pos = e * 32 + lane;
+                            if (pos < p.k) out[pos] = key[e];
+                        }
+                    } else {
+                        kth = warp_compact_mem<E>(b, p.k);
+                        for (int pos = lane; pos < p.k; pos += 32)
+                            out[pos] = __ldcg(reinterpret_cast<const unsigned long long*>(b + pos));
                     }
+                    if (static_cast<int>(lane) == l && kth != 0) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
                 }
                 __syncwarp();
             } else {

@@ -30,6 +30,9 @@ cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured
         case 4: { constexpr int E = 4; return CALL; }      \
         case 8: { constexpr int E = 8; return CALL; }      \
         case 16: { constexpr int E = 16; return CALL; }    \
+        case 32: { constexpr int E = 32; return CALL; }    \
+        case 64: { constexpr int E = 64; return CALL; }    \
+        case 128: { constexpr int E = 128; return CALL; }  \
         default: return cudaErrorInvalidValue;             \
     }
 

@@ -53,7 +53,7 @@ extern "C" {
 #define CVDB_STORE_BF16 0  /* one bf16 plane: bf16 x bf16 -> fp32 tensor-core scores */
 #define CVDB_STORE_EXACT 1 /* three bf16 planes (hi+mid+lo == the fp32 value): fp32-fidelity scores */
 
-#define CVDB_MAX_K 504
+#define CVDB_MAX_K 2048
 
 typedef struct cvdb_index_s* cvdb_index_t;
 

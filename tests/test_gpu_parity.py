@@ -424,6 +424,22 @@ def test_large_database_properties():
     assert torch.equal(Im, I) and torch.equal(Dm, D)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("k", [249, 504, 505, 1016, 1017, 2048])
+def test_large_k_uses_the_in_memory_sort(k, variant):
+    """k > 248: candidate buffers of 1024..4096 keys compacted in place (L2) instead of in registers."""
+    rng = np.random.default_rng(k)
+    n, d, nq = 6000, 48, 270
+    xb, xq = O.bf16_round(unit_rows(rng, n, d)), O.bf16_round(unit_rows(rng, nq, d))
+    xb[4000] = xb[17]                                   # a tie somewhere in the list
+    D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_L2)
+    idx = make_index(d, "l2", "bf16")
+    idx.add(xb)
+    D, I = idx.search(xq, k, force_variant=variant, force_slices=3)
+    idx.close()
+    assert_parity(D, I, D_ref, I_ref, "l2", tie_tol=2e-5)
+
+
 def test_fp16_inputs():
     """float16 rows / queries (numpy or torch, host or device) are converted on the way in."""
     rng = np.random.default_rng(92)
