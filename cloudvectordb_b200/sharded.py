@@ -107,3 +107,60 @@ class ShardedIndex:
         if host_io:
             return Dm.cpu(), Im.cpu()
         return Dm, Im
+
+
+class ShardedIVFFlat:
+    """IVF-Flat over row shards: every rank holds the same coarse quantizer (centroids) and the inverted
+    lists of ITS rows; a search probes the same lists on every rank, scans the local parts, and merges the
+    per-rank candidates like ShardedIndex (one all-gather + k-way select).  Global ids are the
+    concatenation of the shards in rank order."""
+
+    def __init__(self, d: int, nlist: int, metric: str = "l2", device: Optional[int] = None, group=None):
+        from .ivf import IndexIVFFlat
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device, self.metric, self.nlist = device, metric.lower(), int(nlist)
+        self.local = IndexIVFFlat(d, nlist, metric, device)
+        self.nprobe = 1
+        self.id_base, self._ntotal = 0, 0
+
+    def train(self, x_local, niter: int = 10, seed: int = 42, centroids=None) -> None:
+        """Distributed k-means over the ranks' points (sums / counts all-reduced), or adopt given centroids."""
+        if centroids is None:
+            from .kmeans import Kmeans
+            km = Kmeans(self.local.d, self.nlist, niter=niter, seed=seed, device=self.device, group=self.group)
+            km.train(self.local._to_device(x_local))
+            centroids = km.centroids
+        self.local.train(None, centroids=centroids)
+
+    def add_local(self, x_shard) -> None:
+        self.local.add(x_shard)
+        n_loc = int(self.local.ntotal)
+        counts = [n_loc]
+        if self.world > 1:
+            counts = [None] * self.world
+            dist.all_gather_object(counts, n_loc, group=self.group)
+        self.id_base = sum(int(c) for c in counts[: self.rank])
+        self._ntotal = sum(int(c) for c in counts)
+
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def search(self, q, k: int, nprobe: Optional[int] = None):
+        qd = self.local._to_device(q)
+        D, I = self.local.search(qd, k, nprobe=nprobe or self.nprobe)
+        I = torch.where(I >= 0, I + self.id_base, I)
+        if self.world == 1:
+            return D, I
+        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
+        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
+        return merge_topk(Dg, Ig, k, self.metric)
+
+    def close(self) -> None:
+        self.local.close()

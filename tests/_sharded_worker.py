@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from cloudvectordb_b200 import IndexFlat, Kmeans, ShardedIndex, mine_hard_negatives, mine_hard_negatives_sharded  # noqa: E402
+from cloudvectordb_b200 import IndexFlat, IndexIVFFlat, Kmeans, ShardedIndex, ShardedIVFFlat, mine_hard_negatives, mine_hard_negatives_sharded  # noqa: E402
 from cloudvectordb_b200.sharded import shard_bounds  # noqa: E402
 
 
@@ -55,6 +55,20 @@ def main():
     shm.set_groups_local(grp[lo:hi])
     D2, I2 = mine_hard_negatives_sharded(shm, emb[lo:hi].to(dev), km_, grp[lo:hi].to(dev), chunk=3000)
     assert torch.equal(I2, I1[lo:hi]) and torch.equal(D2, D1[lo:hi]), "sharded mining != single GPU"
+    # sharded IVF == single-GPU IVF with the same centroids (same lists probed, union of the shards' rows)
+    cent = emb[:64].float()
+    one = IndexIVFFlat(dm, 64, "ip", device=local)
+    one.train(None, centroids=cent)
+    one.add(emb.to(dev))
+    Dv, Iv = one.search(emb[:500].to(dev), 10, nprobe=5)
+    one.close()
+    shv = ShardedIVFFlat(dm, 64, "ip", device=local)
+    shv.train(None, centroids=cent)
+    shv.add_local(emb[lo:hi].to(dev))
+    assert shv.ntotal == m
+    Dw, Iw = shv.search(emb[:500].to(dev), 10, nprobe=5)
+    assert torch.equal(Iw, Iv) and torch.equal(Dw, Dv), "sharded IVF != single GPU IVF"
+    shv.close()
     # k-means: sharded points, all-reduced update == single-rank update on all points
     pts = torch.nn.functional.normalize(torch.randn((40_000, 64), generator=g), dim=1).bfloat16()
     cent = pts[:128].float()
