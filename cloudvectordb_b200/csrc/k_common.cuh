@@ -8,7 +8,8 @@ namespace cvdb {
 // `configured` is a per-kernel bit mask over device ordinals: the opt-in to > 48 KB of dynamic shared
 // memory is a per-device function attribute.
 template <typename Kern, typename... Args>
-cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured, int grid, cudaStream_t st, Args... args) {
+cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured, int grid, int block, cudaStream_t st,
+                          Args... args) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -18,7 +19,7 @@ cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured
         if (e != cudaSuccess) return e;
         configured |= bit;
     }
-    kern<<<grid, 256, smem, st>>>(args...);
+    kern<<<grid, block, smem, st>>>(args...);
     return cudaGetLastError();
 }
 
