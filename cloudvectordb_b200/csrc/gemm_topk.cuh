@@ -888,7 +888,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         uint32_t acc_phase = 0;
         const int dbg = p.dbg;
         LaneTopk<E> st;
-        uint64_t* const warp_cand = p.cand + ((static_cast<size_t>(blockIdx.x) * p.epi_groups + ewg) * 128 + ewarp * 32) * C;
+        uint64_t* const warp_cand = p.cand + ((static_cast<size_t>(blockIdx.x) * 2 + ewg) * 128 + ewarp * 32) * C;
         if constexpr (E > 0) st.buf = warp_cand + static_cast<size_t>(lane) * C;
         for (int w = pair; w < n_items; w += n_pairs) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
