@@ -346,7 +346,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.q_tiles = static_cast<int>(ceil_div(nq, q_tile));
     p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, block_n));
     // keep the per-slice result scratch under ~1 GiB
-    const int64_t max_slices = std::max<int64_t>(1, (int64_t(1) << 29) / std::max<int64_t>(1, nq * k * 8));
+    const int64_t max_slices = std::max<int64_t>(1, (int64_t(1) << 30) / std::max<int64_t>(1, nq * k * 8));
     if (opts && opts->force_slices > 0) {
         const int64_t s = std::min<int64_t>(opts->force_slices, p.n_tiles);
         p.tiles_per_slice = static_cast<int>(ceil_div(p.n_tiles, s));
@@ -359,13 +359,8 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.self_ids = self_ids;
     p.group_q = group_q;
     p.group_db = (group_q && ix->has_groups) ? ix->groups.as<int32_t>() : nullptr;
-    // resident-query kernel: a second epilogue group when the per-tile MMA time is short (K <= 256) and the
-    // selection is light (k <= 28); it then keeps two result lists per slice
-    const bool two_groups = (variant == 2 || variant == 4) && p.nkb <= 4 && k <= 28 && !(opts && (opts->debug_flags & 32));
-    p.epi_groups = two_groups ? 2 : 1;
-    p.part_lists = p.n_slices * p.epi_groups;
-    if (E > 0) TRY(ix->cand.ensure(static_cast<size_t>(grid) * (two_groups ? 2 : 1) * 128 * C * 8));
-    TRY(ix->part.ensure(static_cast<size_t>(nq) * p.part_lists * k * 8));
+    if (E > 0) TRY(ix->cand.ensure(static_cast<size_t>(grid) * 128 * C * 8));
+    TRY(ix->part.ensure(static_cast<size_t>(nq) * p.n_slices * k * 8));
     p.cand = ix->cand.as<uint64_t>();
     p.part = ix->part.as<uint64_t>();
     TRY(ix->gthr.ensure(static_cast<size_t>(nq) * 4));
@@ -414,11 +409,11 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
 
     const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
     if (I64)
-        merge_partials_kernel<int64_t><<<blocks, 256, 8 * p.part_lists * sizeof(uint16_t), st>>>(
-            p.part, nq, p.part_lists, k, k, l2, ix->q_norm.as<float>(), id_base, D, I64);
+        merge_partials_kernel<int64_t><<<blocks, 256, 8 * p.n_slices * sizeof(uint16_t), st>>>(
+            p.part, nq, p.n_slices, k, k, l2, ix->q_norm.as<float>(), id_base, D, I64);
     else
-        merge_partials_kernel<int32_t><<<blocks, 256, 8 * p.part_lists * sizeof(uint16_t), st>>>(
-            p.part, nq, p.part_lists, k, k, l2, ix->q_norm.as<float>(), id_base, D, I32);
+        merge_partials_kernel<int32_t><<<blocks, 256, 8 * p.n_slices * sizeof(uint16_t), st>>>(
+            p.part, nq, p.n_slices, k, k, l2, ix->q_norm.as<float>(), id_base, D, I32);
     ++g_launches;
     CU_TRY(cudaGetLastError());
 

@@ -232,7 +232,7 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
 // End of a work item: sorted top-k of every query of the warp -> part[q][slice][0..k).
 template <int E>
 __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams& p, int q_base, int q_row, bool q_valid,
-                                           int list) {
+                                           int slice) {
     const uint32_t lane = threadIdx.x & 31;
     if constexpr (E > 0) {
         __syncwarp();
@@ -240,7 +240,7 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
             const int qr = q_base + l;
             if (qr >= p.nq) break;
             uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
-            uint64_t* out = p.part + (static_cast<size_t>(qr) * p.part_lists + list) * p.k;
+            uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
             uint64_t kth;
             if constexpr (E <= 16) {
                 uint64_t key[E];
@@ -259,7 +259,7 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
         }
         __syncwarp();
     } else {
-        if (q_valid) p.part[static_cast<size_t>(q_row) * p.part_lists + list] = st.best;
+        if (q_valid) p.part[static_cast<size_t>(q_row) * p.n_slices + slice] = st.best;
     }
 }
 
@@ -704,7 +704,7 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // L2 -> SM traffic per SM is a third of the streaming kernel's.
 // ===========================================================================
 template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES, int E>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                      const __nv_bfloat16* __restrict__ q_pack, const int q_row_elems, const GemmTopkParams p) {
     constexpr int HALF_N = BLOCK_N / 2;                    // database rows this CTA loads per tile
@@ -746,7 +746,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 8 * p.epi_groups);  // epilogue groups x 4 warps x 2 CTAs
+            mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
         }
         mbar_init(a_ready, KB_S > 0 ? 9 : 8);  // + the leader producer's expect_tx for the tails
         mbar_init(a_free, 1);
@@ -875,21 +875,16 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
             }
         }
-    } else if (warp >= 4 && (warp - 4) < 4 * p.epi_groups) {
+    } else if (warp >= 4) {
         // ----------------------------------------------------------- epilogue (both CTAs)
-        // One or two epilogue groups of four warps (p.epi_groups): group g scans its share of the columns of
-        // every accumulator for all 128 query rows, with its own candidate buffers and result list (thresholds
-        // meet through gthr).  For small K and small k the scan, not the MMA, bounds a tile and two groups pay
-        // (d=128, k=10: +14 %); for K=768 one group is enough and the second would only cost power (-0.9 %).
-        const int ewg = (warp - 4) >> 2;
-        const int ewarp = (warp - 4) & 3;   // == warp % 4: TMEM lanes [32*ewarp, 32*ewarp + 32)
+        const int ewarp = warp - 4;
         const uint32_t lane_base = static_cast<uint32_t>(ewarp * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
         const int dbg = p.dbg;
         LaneTopk<E> st;
-        uint64_t* const warp_cand = p.cand + ((static_cast<size_t>(blockIdx.x) * 2 + ewg) * 128 + ewarp * 32) * C;
-        if constexpr (E > 0) st.buf = warp_cand + static_cast<size_t>(lane) * C;
+        if constexpr (E > 0)
+            st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32 + lane) * C;
         for (int w = pair; w < n_items; w += n_pairs) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
             const int t0 = slice * p.tiles_per_slice;
@@ -897,10 +892,10 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const int q_base = qt * 256 + static_cast<int>(rank) * 128 + ewarp * 32;
             const int q_row = q_base + lane;
             const bool q_valid = q_row < p.nq;
-            // ---- (1) this thread's query row -> TMEM lane (bf16 pairs, 16 columns per store); group 0 only.
+            // ---- (1) this thread's query row -> TMEM lane (bf16 pairs, 16 columns per store).
             // Safe to overwrite: the previous item's last accumulator was consumed, so all
             // MMAs that read the old rows have retired.
-            if (ewg == 0) {
+            {
                 const uint4* src = reinterpret_cast<const uint4*>(q_pack + static_cast<size_t>(q_valid ? q_row : 0) * q_row_elems);
                 const int n_vec = q_valid ? (min(q_row_elems, nkb_t * 64) >> 3) : 0;  // 16-byte granules with data
                 for (int c16 = 0; c16 < nkb_t * 2; ++c16) {
@@ -921,22 +916,20 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
-            item_begin<E>(st, p, q_row, q_valid, warp_cand);
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
                 const uint32_t taddr = tmem_base + lane_base + A_COLS + acc * BLOCK_N;
-                const int c_span = BLOCK_N / p.epi_groups;
-                const int c_begin = ewg * c_span, c_end = c_begin + c_span;
 #pragma unroll 1
-                for (int c = c_begin; c < c_end; c += 32) {
+                for (int c = 0; c < BLOCK_N; c += 32) {
                     uint32_t v[32];
                     if (!(dbg & 2)) {
                         tmem_ld32(taddr + c, v);
                         tmem_ld_wait();
                     }
-                    if (c + 32 == c_end) {
+                    if (c + 32 == BLOCK_N) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
@@ -947,7 +940,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            item_flush<E>(st, p, q_base, q_row, q_valid, slice * p.epi_groups + ewg);
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice);
         }
     }
 

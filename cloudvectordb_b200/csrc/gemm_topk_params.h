@@ -13,8 +13,6 @@ struct GemmTopkParams {
     int q_tiles;          // ceil(nq / 128)
     int n_tiles;          // ceil(n_rows / BLOCK_N)
     int n_slices;         // database slices
-    int part_lists;       // result lists per query in `part`: n_slices * epi_groups
-    int epi_groups;       // resident-query kernel: 1 or 2 epilogue groups share the columns of every accumulator
     int tiles_per_slice;  // in BLOCK_N units
     int nkb;              // 64-element K blocks per plane
     int k16;              // 16-element MMA K steps per plane (ceil(Kp / 16)): the last K block may need fewer than 4
@@ -26,7 +24,7 @@ struct GemmTopkParams {
     const int32_t* group_q;   // [nq] group id per query (<0: none), or null
     const int32_t* group_db;  // [n_rows] group id per database row, or null
     uint64_t* cand;  // [gridDim.x][128][32*E] candidate scratch (E>0)
-    uint64_t* part;  // [nq][part_lists][k] per-slice results (keys)
+    uint64_t* part;  // [nq][n_slices][k] per-slice results (keys)
     uint32_t* gthr;  // [nq] shared per-query threshold (ordered-float), zeroed before the launch
     uint32_t* wave_cnt;  // [waves] producers that finished issuing the loads of their item in that wave (or null)
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too

@@ -8,8 +8,7 @@ namespace cvdb {
 // `configured` is a per-kernel bit mask over device ordinals: the opt-in to > 48 KB of dynamic shared
 // memory is a per-device function attribute.
 template <typename Kern, typename... Args>
-cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured, int grid, int block, cudaStream_t st,
-                          Args... args) {
+cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured, int grid, cudaStream_t st, Args... args) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -19,7 +18,7 @@ cudaError_t launch_kernel(Kern kern, size_t smem, unsigned long long& configured
         if (e != cudaSuccess) return e;
         configured |= bit;
     }
-    kern<<<grid, block, smem, st>>>(args...);
+    kern<<<grid, 256, smem, st>>>(args...);
     return cudaGetLastError();
 }
 

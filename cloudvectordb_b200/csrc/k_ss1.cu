@@ -4,7 +4,7 @@ namespace cvdb {
 template <int E>
 static cudaError_t go(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid, cudaStream_t st) {
     static unsigned long long configured = 0;
-    return launch_kernel(gemm_topk_ss_kernel<256, 4, E>, gemm_topk_ss_smem_bytes<256, 4>(), configured, grid, 256, st, tq, tx, p);
+    return launch_kernel(gemm_topk_ss_kernel<256, 4, E>, gemm_topk_ss_smem_bytes<256, 4>(), configured, grid, st, tq, tx, p);
 }
 cudaError_t launch_ss1(int E_, const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid,
                        cudaStream_t st) {

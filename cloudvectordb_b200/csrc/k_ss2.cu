@@ -4,7 +4,7 @@ namespace cvdb {
 template <int E>
 static cudaError_t go(const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid, cudaStream_t st) {
     static unsigned long long configured = 0;
-    return launch_kernel(gemm_topk_ss2_kernel<256, 6, E>, gemm_topk_ss2_smem_bytes<256, 6>(), configured, grid, 256, st, tq, tx, p);
+    return launch_kernel(gemm_topk_ss2_kernel<256, 6, E>, gemm_topk_ss2_smem_bytes<256, 6>(), configured, grid, st, tq, tx, p);
 }
 cudaError_t launch_ss2(int E_, const CUtensorMap& tq, const CUtensorMap& tx, const GemmTopkParams& p, int grid,
                        cudaStream_t st) {

@@ -69,7 +69,7 @@ typedef struct cvdb_search_opts {
     int force_variant;       /* 0: auto; 1..4: force that kernel variant (cvdb_index_last_variant)   */
     int debug_flags;         /* kernel-tuning experiments only (results become invalid): 1 = skip the
                                 top-k scan, 2 = skip the TMEM read as well, 4 = no threshold sharing between slices,
-                                8 = no wave alignment of the producers, 32 = never use a second epilogue group */
+                                8 = no wave alignment of the producers */
 } cvdb_search_opts;
 
 /* -- index lifetime -------------------------------------------------------

@@ -137,21 +137,6 @@ def test_threshold_sharing_is_result_neutral():
     assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
 
 
-def test_second_epilogue_group_is_result_neutral():
-    """K <= 256 and k <= 28 run two epilogue groups in the resident-query kernel (debug flag 32 = one group)."""
-    rng = np.random.default_rng(79)
-    n, d, nq, k = 50000, 128, 600, 10
-    xb, xq = O.bf16_round(unit_rows(rng, n, d)), O.bf16_round(unit_rows(rng, nq, d))
-    D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_L2)
-    idx = make_index(d, "l2", "bf16")
-    idx.add(xb)
-    D0, I0 = idx.search(xq, k, force_variant=2)
-    D1, I1 = idx.search(xq, k, force_variant=2, debug_flags=32)
-    idx.close()
-    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
-    assert_parity(D0, I0, D_ref, I_ref, "l2", tie_tol=2e-5)
-
-
 @pytest.mark.parametrize("slices", [2, 3, 7, 40])
 def test_database_slices_do_not_change_results(slices):
     rng = np.random.default_rng(slices)
