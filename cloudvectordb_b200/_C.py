@@ -65,6 +65,7 @@ SIGNATURES = {
     "cvdb_index_row_bytes": (C.c_int64, [C.c_void_p]),
     "cvdb_index_export_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cvdb_index_import_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cvdb_plan_slices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cvdb_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_void_p]),
     "cvdb_kmeans_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -968,6 +968,12 @@ int cvdb_index_import_rows(cvdb_index_t h, const void* host_src, int64_t nrows, 
     return CVDB_OK;
 }
 
+int cvdb_plan_slices(int q_tiles, int n_tiles, int workers, int64_t max_slices, int* n_slices, int* tiles_per_slice) {
+    if (q_tiles < 1 || n_tiles < 1 || workers < 1 || !n_slices || !tiles_per_slice) return fail(CVDB_EINVAL, "bad arguments");
+    choose_slices(q_tiles, n_tiles, workers, max_slices, *n_slices, *tiles_per_slice);
+    return CVDB_OK;
+}
+
 int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric, float* D,
                     int64_t* I, int on_device, void* stream) {
     if (nq < 0 || nlists < 1 || k_in < 1 || k < 1) return fail(CVDB_EINVAL, "bad sizes");

@@ -151,6 +151,12 @@ int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int
 /* centroids[j] = sums[j] / counts[j] where counts[j] > 0 (else unchanged).  Device pointers only. */
 int cvdb_kmeans_finalize(const float* sums, const int32_t* counts, int K, int d, float* centroids, void* stream);
 
+/* -- host-side planning (no GPU needed; exposed for tests) -----------------------------------------
+ * How a search splits the database: work item = (query tile, database slice).  Given the number of query tiles,
+ * database tiles and workers (CTAs or CTA pairs), returns the slice count and tiles per slice that minimise
+ * waves * (tiles per slice + per-item overhead), with at most max_slices slices. */
+int cvdb_plan_slices(int q_tiles, int n_tiles, int workers, int64_t max_slices, int* n_slices, int* tiles_per_slice);
+
 /* -- diagnostics ------------------------------------------------------------ */
 const char* cvdb_last_error(void);
 int64_t cvdb_kernel_launches(void); /* kernels launched by this library so far (process-wide) */

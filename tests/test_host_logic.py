@@ -67,6 +67,34 @@ def test_argument_validation_without_gpu():
             IndexFlatIP(8)
 
 
+def test_slice_planner_properties():
+    lib = _C.lib()
+
+    def plan(qt, nt, w, mx=1 << 40):
+        a, b = C.c_int(), C.c_int()
+        assert lib.cvdb_plan_slices(qt, nt, w, mx, C.byref(a), C.byref(b)) == 0
+        return a.value, b.value
+
+    import math
+    for qt, nt, w in [(1, 1, 148), (40, 78125, 74), (79, 39063, 148), (1, 48829, 148), (512, 24415, 74), (3, 7, 74),
+                      (40, 9766, 74), (1000, 5, 148)]:
+        s, tps = plan(qt, nt, w)
+        assert 1 <= s <= nt and tps >= 1
+        assert (s - 1) * tps < nt <= s * tps                      # the slices cover every tile, none is empty
+        waves = math.ceil(qt * s / w)
+        cost, cost_one = waves * (tps + 4), math.ceil(qt / w) * (nt + 4)
+        assert cost <= cost_one                                   # never worse than not slicing at all
+        ideal = qt * nt / w
+        if qt * nt >= 50 * w:
+            assert cost <= 1.08 * ideal + 8                       # close to perfectly balanced for big problems
+    # headline shape: 40 query tiles x 74 CTA pairs -> 37 slices, 20 whole waves
+    assert plan(40, 78125, 74)[0] == 37
+    # a scratch budget caps the number of slices
+    s, tps = plan(40, 78125, 74, 5)
+    assert s <= 5 and (s - 1) * tps < 78125 <= s * tps
+    assert lib.cvdb_plan_slices(0, 5, 74, 10, C.byref(C.c_int()), C.byref(C.c_int())) == _C.EINVAL
+
+
 def test_shard_bounds_partition():
     for n in (0, 1, 7, 8, 100, 10_000_001):
         for w in (1, 2, 3, 8):
