@@ -239,8 +239,7 @@ int pick_E(int k) {
 
 // Split the database into slices so that (query tiles x slices) fills the grid
 // in whole waves.  Cost model: waves * (tiles per slice + fixed per-item overhead).
-void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& n_slices, int& tps) {
-    const int ovh = 4;
+void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& n_slices, int& tps, int ovh = 4) {
     int64_t best = INT64_MAX;
     n_slices = 1;
     tps = n_tiles;
@@ -352,7 +351,11 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         p.tiles_per_slice = static_cast<int>(ceil_div(p.n_tiles, s));
         p.n_slices = static_cast<int>(ceil_div(p.n_tiles, p.tiles_per_slice));
     } else {
-        choose_slices(p.q_tiles, p.n_tiles, workers, max_slices, p.n_slices, p.tiles_per_slice);
+        // per-item overhead in tile times: the resident-query kernel reloads its queries into TMEM and drains
+        // the pipeline at every item boundary (~10 us), the streaming kernels only flush their results
+        int ovh = (variant == 2 || variant == 4) ? 8 : 4;
+        if (const char* env = getenv("CVDB_PLAN_OVH")) ovh = atoi(env);  // tuning experiments
+        choose_slices(p.q_tiles, p.n_tiles, workers, max_slices, p.n_slices, p.tiles_per_slice, ovh);
     }
     const int64_t n_items = static_cast<int64_t>(p.q_tiles) * p.n_slices;
     const int grid = static_cast<int>(std::min<int64_t>(workers, n_items)) * (variant == 1 ? 1 : 2);
