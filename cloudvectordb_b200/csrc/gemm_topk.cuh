@@ -835,6 +835,31 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         tc_fence_after();
                         if (elect_one_sync()) {
                             const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b + stage * STAGE_BYTES));
+                            // Fast path: a whole stage of full K blocks, all served from TMEM or all from the
+                            // tail -> 4*KB_STAGE MMAs with compile-time operand offsets (the issue loop, not the
+                            // tensor pipe, bounded short-K tiles: ncu showed the pipe 81 % active at K = 384).
+                            const bool whole = (kb1 - kb0 == KB_STAGE) && (p.k16 >= 4 * kb1);
+                            if (whole && (KB_S == 0 || kb1 <= KB_T)) {
+                                const uint32_t a0 = tmem_base + kb0 * 32;
+#pragma unroll
+                                for (int i = 0; i < KB_STAGE; ++i) {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_ts<2>(tmem_d, a0 + i * 32 + kk * 8,
+                                                   b_desc0 + static_cast<uint64_t>(((i * KB_BYTES) >> 4) + 2 * kk), idesc,
+                                                   (i | kk) != 0 ? 1u : static_cast<uint32_t>(g != 0));
+                                }
+                            } else if (whole && KB_S > 0 && kb0 >= KB_T) {
+                                const uint64_t a_desc0 =
+                                    make_smem_desc_sw128(smem_u32(smem_tail + (kb0 - KB_T) * TAIL_KB_BYTES));
+#pragma unroll
+                                for (int i = 0; i < KB_STAGE; ++i) {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_ss<2>(tmem_d, a_desc0 + static_cast<uint64_t>(((i * TAIL_KB_BYTES) >> 4) + 2 * kk),
+                                                   b_desc0 + static_cast<uint64_t>(((i * KB_BYTES) >> 4) + 2 * kk), idesc, 1u);
+                                }
+                            } else
                             for (int kb = kb0; kb < kb1; ++kb) {
                                 const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(((kb - kb0) * KB_BYTES) >> 4);
                                 // the last K block may be partly padding: issue only the K=16 steps that hold data
