@@ -374,10 +374,13 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
                         const int kb = s % p.nkb;
                         const int nk = min(4, p.k16 - 4 * kb);  // the last K block of a plane may be partly padding
+                        if (nk == 4) {
 #pragma unroll
-                        for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                            // +32 bytes along K inside the 128-byte swizzled row
-                            if (kk < nk) umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                            for (int kk = 0; kk < 4; ++kk)  // +32 bytes along K inside the 128-byte swizzled row
+                                umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                        } else {
+                            for (int kk = 0; kk < nk; ++kk)
+                                umma_ss<1>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
                         }
                         umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                         if (s == ksteps - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -1097,9 +1100,14 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
                             const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
                             const int nk = min(4, p.k16 - 4 * (s % p.nkb));
+                            if (nk == 4) {
 #pragma unroll
-                            for (int kk = 0; kk < BLOCK_K / 16; ++kk)
-                                if (kk < nk) umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                            } else {
+                                for (int kk = 0; kk < nk; ++kk)
+                                    umma_ss<2>(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (s | kk) != 0);
+                            }
                             umma_commit_2sm(&empty_bar[stage], 3);
                             if (s == ksteps - 1) umma_commit_2sm(&tmem_full[acc], 3);
                         }
