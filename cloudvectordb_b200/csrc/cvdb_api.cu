@@ -326,7 +326,15 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage),
     //   4 = CTA pair with all of K <= 768 in TMEM and 64-column accumulators (comparison only).
     const bool ts2_ok = ix->planes == 1 && p.nkb <= 13;  // padded K <= 832 (768 + the L2 norm columns)
-    int variant = (ts2_ok && nq > 256) ? 2 : 1;
+    int variant = 1;
+    if (ts2_ok && nq > 256) {
+        // large batches: resident queries win for K >= 448 and for k = 1; for short K with a real top-k the
+        // 256 x 256 streaming pair kernel is ahead (K = 384, k = 10: 1325 vs 1236 TFLOP/s), and for K <= 128 the
+        // single-CTA kernel (841 vs 804 / 707) -- tools/variant_sweep.py
+        if (p.nkb <= 2) variant = 1;
+        else if (p.nkb <= 6 && k > 1) variant = 3;
+        else variant = 2;
+    }
     if (opts && opts->force_variant == 1) variant = 1;
     if (opts && opts->force_variant == 3) variant = 3;
     if (opts && opts->force_variant == 2) {
