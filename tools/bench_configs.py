@@ -45,7 +45,7 @@ def emit(f, **kw):
     f.flush()
 
 
-def mining(f, peaks, rows=6_250_000, d=768, chunk=65536, k=50, variant=int(os.environ.get("CVDB_VARIANT", "0"))):
+def mining(f, peaks, rows=6_250_000, d=768, chunk=65536, k=int(os.environ.get("CVDB_K", "50")), variant=int(os.environ.get("CVDB_VARIANT", "0"))):
     """configs[2]: 50M x 768 self-join top-50 with positive exclusion over 8 GPUs -> 6.25M rows per GPU;
     one step = one 65 536-anchor chunk against the local shard."""
     xb = gen_rows(torch, DEV, 1234, 0, rows, d, torch.bfloat16)
@@ -57,7 +57,9 @@ def mining(f, peaks, rows=6_250_000, d=768, chunk=65536, k=50, variant=int(os.en
     q = xb[:chunk]
     self_ids = torch.arange(chunk, device=DEV, dtype=torch.int32)
     gq = groups[:chunk]
-    ms, (D, I) = timed(lambda: idx.search(q, k, self_ids=self_ids, group_q=gq, profile=True, force_variant=variant))
+    excl = os.environ.get("CVDB_NOEXCL") is None
+    ms, (D, I) = timed(lambda: idx.search(q, k, self_ids=self_ids if excl else None, group_q=gq if excl else None,
+                                          profile=True, force_variant=variant))
     kms = idx.profile_ms()
     w = idx.last_work()
     ok_self = bool((I != self_ids[:, None].long()).all())
