@@ -226,6 +226,10 @@ constexpr int kBlockN = 256;
 // buffer) is needed only once per ~k accepted rows.  Up to 512 slots the sort runs in registers; larger buffers
 // (k > 248) are sorted in place in L2-resident memory.
 int pick_E(int k) {
+    if (const char* env = getenv("CVDB_E_MULT")) {  // experiments: size the buffer as if k were larger
+        const int m = atoi(env);
+        if (m > 1 && k > 1) k = std::min(k * m, 248);
+    }
     if (k == 1) return 0;
     if (k <= 12) return 1;
     if (k <= 28) return 2;
@@ -235,6 +239,17 @@ int pick_E(int k) {
     if (k <= 504) return 32;
     if (k <= 1016) return 64;
     return 128;
+}
+
+// Candidates a buffer of C slots may hold before it is compacted: k + max(8, k/2), at most C - 8 (eight free
+// slots are needed before each group of eight scores).  CVDB_ROOM_EXTRA overrides the k/2 (experiments).
+int compaction_trigger(int k, int C) {
+    if (C > 512) return C - 8;  // in-memory sorts (k > 248) are expensive: compact as rarely as possible
+    // measured (mining shape, k = 50): compacting earlier than necessary is slower (500 / 524 / 550 ms for
+    // C-8 / k+25 / k+12) -- a compaction stalls the warp on L2 round trips -- so fill the buffer.
+    int room = C - 8;
+    if (const char* env = getenv("CVDB_ROOM_EXTRA")) room = std::min(C - 8, k + std::max(1, atoi(env)));
+    return room;
 }
 
 // Split the database into slices so that (query tiles x slices) fills the grid
@@ -305,6 +320,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.nq = static_cast<int>(nq);
     p.n_rows = static_cast<int>(ix->ntotal);
     p.k = k;
+    p.room = compaction_trigger(k, C);
     p.dbg = opts ? opts->debug_flags : 0;
     p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
     p.k16 = (opts && (opts->debug_flags & 16)) ? 4 * p.nkb : static_cast<int>(ceil_div(ix->Kd, 16));
@@ -501,6 +517,7 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
         GroupedParams p{};
         p.n_items_ptr = ix->ivf_scal.as<int32_t>();
         p.k = k;
+        p.room = compaction_trigger(k, C);
         p.nkb = static_cast<int>(ceil_div(ix->Kp, 64));
         p.k16 = static_cast<int>(ceil_div(ix->Kd, 16));
         p.items = reinterpret_cast<const GroupItem*>(ix->ivf_items.p);

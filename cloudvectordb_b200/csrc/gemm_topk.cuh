@@ -146,10 +146,12 @@ __device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k) {
     return __ldcg(reinterpret_cast<const unsigned long long*>(b + k - 1));
 }
 
+// `room`: compact once a buffer holds more than this many candidates.  Between compactions the threshold is
+// stale (it admits rows that the next sort throws away again), so compacting well before the buffer is full
+// -- k + max(8, k/2) instead of 32*E - 8 -- trades a few more sorts for fewer trips through the slow path.
 template <int E, bool strict_own = true>
-__device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
-    constexpr int C = 32 * E;
-    unsigned mask = __ballot_sync(0xffffffffu, st.cnt > C - 8);
+__device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room) {
+    unsigned mask = __ballot_sync(0xffffffffu, st.cnt > room);
     if (mask == 0) return;
     __syncwarp();
     const uint32_t lane = threadIdx.x & 31;
@@ -177,7 +179,7 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k) {
 // groups of 8 in which some lane has a candidate are walked element by element.
 template <int E>
 __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0, uint32_t row_end,
-                                           uint32_t self, int grp, const int32_t* __restrict__ group_db, int k) {
+                                           uint32_t self, int grp, const int32_t* __restrict__ group_db, int k, int room) {
     float m8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -191,7 +193,7 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
-        if constexpr (E > 0) make_room<E>(st, k);
+        if constexpr (E > 0) make_room<E>(st, k, room);
 #pragma unroll
         for (int j = 8 * g; j < 8 * g + 8; ++j) {
             const float s = __uint_as_float(v[j]);
@@ -429,7 +431,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         mbar_arrive(&tmem_empty[acc]);
                     }
                     if (!(dbg & 3))
-                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -460,7 +462,7 @@ constexpr size_t gemm_topk_ss_smem_bytes() {
 // ===========================================================================
 template <int E>
 __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0,
-                                                   uint32_t row_end, const int32_t* __restrict__ row_ids, int k) {
+                                                   uint32_t row_end, const int32_t* __restrict__ row_ids, int k, int room) {
     float m8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -475,7 +477,7 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
     for (int g = 0; g < 4; ++g) {
         if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
         // rows of a list are stored in no particular id order: equal scores must stay candidates (keys decide)
-        if constexpr (E > 0) make_room<E, false>(st, k);
+        if constexpr (E > 0) make_room<E, false>(st, k, room);
 #pragma unroll
         for (int j = 8 * g; j < 8 * g + 8; ++j) {
             const float s = __uint_as_float(v[j]);
@@ -642,7 +644,7 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         tc_fence_before();
                         mbar_arrive(&tmem_empty[acc]);
                     }
-                    scan_chunk_grouped<E>(st, v, row0 + c, row_end, p.row_ids, p.k);
+                    scan_chunk_grouped<E>(st, v, row0 + c, row_end, p.row_ids, p.k, p.room);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -963,7 +965,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
                     }
                     if (!(dbg & 3))
-                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -1157,7 +1159,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
                     }
                     if (!(dbg & 3))
-                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k);
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;

@@ -10,6 +10,7 @@ struct GemmTopkParams {
     int nq;               // queries in this launch
     int n_rows;           // database rows in this launch
     int k;                // results kept per (query, slice); k <= 32*E - 8 (E>0) or 1 (E==0)
+    int room;             // compact a query's buffer once it holds more than this many candidates (<= 32*E - 8)
     int q_tiles;          // ceil(nq / 128)
     int n_tiles;          // ceil(n_rows / BLOCK_N)
     int n_slices;         // database slices
@@ -38,6 +39,7 @@ struct GroupItem {
 };
 
 struct GroupedParams {
+    int room;                // compaction trigger, as in GemmTopkParams
     const int* n_items_ptr;  // device scalar: number of work items (written by the bucketing kernels)
     int k;
     int nkb, k16;
