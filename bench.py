@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--metric", default="ip", choices=["ip", "l2"])
+    ap.add_argument("--dist", default="iid", choices=["iid", "clustered"],
+                    help="iid: unit-norm Gaussian rows; clustered: 4096 centres + 0.3 noise, queries = rows + 0.1 noise")
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="database rows of the bounded CPU sample")
     ap.add_argument("--cpu-nq", type=int, default=2048, help="queries of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,7 +64,9 @@ def workload_name(a):
 
 def workload_config(a, world):
     return {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "queries_per_step": a.nq,
-            "k": a.k, "metric": a.metric, "distribution": "iid unit-norm Gaussian rows, seeds 1234/5678",
+            "k": a.k, "metric": a.metric,
+            "distribution": ("iid unit-norm Gaussian rows" if a.dist == "iid" else
+                             "clustered: 4096 centres + 0.3 noise, queries = rows + 0.1 noise") + ", seeds 1234/5678",
             "sharding": f"rows split over {world} rank(s), one all-gather of (D,I) + k-way select",
             "cache": "inputs larger than L2 (database 15.4 GB vs 126 MB L2), no explicit flush"}
 
@@ -174,13 +178,18 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- GPU arm
-def gen_rows(torch, dev, seed, lo, hi, d, dtype):
-    """Rows [lo, hi) of the synthetic unit-norm matrix; chunk c uses generator seed+c."""
+def gen_rows(torch, dev, seed, lo, hi, d, dtype, centres=None, noise=0.3):
+    """Rows [lo, hi) of the synthetic unit-norm matrix; chunk c uses generator seed+c.
+    With `centres` the rows are centre[random] + noise * N(0, I) (the clustered distribution of SURVEY.md 8(d))."""
     out = torch.empty((hi - lo, d), dtype=dtype, device=dev)
     c0, c1 = lo // CHUNK, (hi - 1) // CHUNK
     for c in range(c0, c1 + 1):
         g = torch.Generator(device=dev).manual_seed(seed + c)
-        blk = torch.nn.functional.normalize(torch.randn((CHUNK, d), generator=g, device=dev), dim=1)
+        blk = torch.randn((CHUNK, d), generator=g, device=dev)
+        if centres is not None:
+            which = torch.randint(0, centres.shape[0], (CHUNK,), generator=g, device=dev)
+            blk = centres[which] + noise * blk
+        blk = torch.nn.functional.normalize(blk, dim=1)
         a, b = max(lo, c * CHUNK), min(hi, (c + 1) * CHUNK)
         out[a - lo:b - lo] = blk[a - c * CHUNK:b - c * CHUNK].to(dtype)
     return out
@@ -205,8 +214,26 @@ def run_ours(a):
     peaks = load_peaks()
 
     lo, hi = shard_bounds(a.rows, world, rank)
-    xb = gen_rows(torch, dev, DB_SEED, lo, hi, a.dim, torch.bfloat16)
-    xq = gen_rows(torch, dev, Q_SEED, 0, a.nq, a.dim, torch.bfloat16)
+    centres = None
+    if a.dist == "clustered":
+        centres = torch.randn((4096, a.dim), generator=torch.Generator(device=dev).manual_seed(99), device=dev)
+    xb = gen_rows(torch, dev, DB_SEED, lo, hi, a.dim, torch.bfloat16, centres)
+    if a.dist == "clustered":   # queries: random database rows (of the whole matrix) plus a little noise
+        gq = torch.Generator(device=dev).manual_seed(Q_SEED)
+        picks = torch.randint(0, a.rows, (a.nq,), generator=gq, device=dev)
+        # regenerate the picked rows chunk-wise (any rank can do it: the generator is seeded per chunk)
+        rows_f32 = torch.empty((a.nq, a.dim), device=dev)
+        order = torch.argsort(picks)
+        sp = picks[order]
+        for c in torch.unique(sp // CHUNK).tolist():
+            blk = gen_rows(torch, dev, DB_SEED, c * CHUNK, (c + 1) * CHUNK, a.dim, torch.float32, centres)
+            m = (sp // CHUNK) == c
+            rows_f32[order[m]] = blk[sp[m] - c * CHUNK]
+        xq32 = torch.nn.functional.normalize(rows_f32 + 0.1 * torch.randn((a.nq, a.dim), generator=gq, device=dev), dim=1)
+        xq = xq32.bfloat16()
+    else:
+        xq32 = None
+        xq = gen_rows(torch, dev, Q_SEED, 0, a.nq, a.dim, torch.bfloat16)
     if world > 1:
         index = ShardedIndex(a.dim, a.metric, "bf16", device=local_rank)
         index.local.reserve(hi - lo)
@@ -322,11 +349,11 @@ def run_ours(a):
     recall = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, ref_i)]))
 
     # the same against fp32 scores of the UNROUNDED fp32 rows and queries (regenerated chunk by chunk)
-    qs32 = gen_rows(torch, dev, Q_SEED, 0, nchk, a.dim, torch.float32)
+    qs32 = xq32[:nchk] if xq32 is not None else gen_rows(torch, dev, Q_SEED, 0, nchk, a.dim, torch.float32)
     bv = torch.full((nchk, a.k), -float("inf"), device=dev)
     bi = torch.full((nchk, a.k), -1, dtype=torch.int64, device=dev)
     for r0 in range(lo, hi, 1 << 20):
-        blk = gen_rows(torch, dev, DB_SEED, r0, min(hi, r0 + (1 << 20)), a.dim, torch.float32)
+        blk = gen_rows(torch, dev, DB_SEED, r0, min(hi, r0 + (1 << 20)), a.dim, torch.float32, centres)
         s = qs32 @ blk.T
         if a.metric == "l2":
             s = -((qs32 * qs32).sum(1)[:, None] - 2 * s + (blk * blk).sum(1)[None, :])
