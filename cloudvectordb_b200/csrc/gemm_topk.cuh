@@ -4,6 +4,12 @@
 //   per query keep the k best (score desc, row asc) -- the score matrix lives
 //   only in TMEM, never in HBM.
 //
+// This file holds the kernel families (see DESIGN.md 4.1 for when each one runs):
+//   gemm_topk_ss_kernel       single CTA, both operands streamed          (variant 1)
+//   gemm_topk_ts2_kernel      CTA pair, queries resident in TMEM / smem   (variants 2 and 4)
+//   gemm_topk_ss2_kernel      CTA pair, both operands streamed            (variant 3)
+//   gemm_topk_grouped_kernel  single CTA, work items from a table (IVF list scan)
+//
 // Roles inside one CTA (256 threads, one CTA per SM, persistent):
 //   warp 0      TMA producer: streams 64-wide K blocks of the query tile (A)
 //               and of the database tile (B) into a STAGES-deep smem ring
@@ -21,7 +27,7 @@
 // CTAs that run concurrently stream the SAME database rows (they hit in L2 and
 // HBM sees each database byte about once per batch).  Every item ends by
 // writing its sorted top-k to part[query][slice][k]; merge_partials_kernel
-// (select_kernels.cuh) does the final k-way select.
+// (aux_kernels.cuh) does the final k-way merge.
 #pragma once
 #include <cuda_bf16.h>
 
