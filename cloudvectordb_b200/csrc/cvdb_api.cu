@@ -241,8 +241,8 @@ int pick_E(int k) {
     return 128;
 }
 
-// Candidates a buffer of C slots may hold before it is compacted: k + max(8, k/2), at most C - 8 (eight free
-// slots are needed before each group of eight scores).  CVDB_ROOM_EXTRA overrides the k/2 (experiments).
+// Candidates a buffer of C slots may hold before it is compacted: C - 8 (eight free slots are needed before
+// each group of eight scores).  CVDB_ROOM_EXTRA = x lowers it to k + x (experiments only).
 int compaction_trigger(int k, int C) {
     if (C > 512) return C - 8;  // in-memory sorts (k > 248) are expensive: compact as rarely as possible
     // measured (mining shape, k = 50): compacting earlier than necessary is slower (500 / 524 / 550 ms for

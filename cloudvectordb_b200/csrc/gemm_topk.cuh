@@ -152,9 +152,9 @@ __device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k) {
     return __ldcg(reinterpret_cast<const unsigned long long*>(b + k - 1));
 }
 
-// `room`: compact once a buffer holds more than this many candidates.  Between compactions the threshold is
-// stale (it admits rows that the next sort throws away again), so compacting well before the buffer is full
-// -- k + max(8, k/2) instead of 32*E - 8 -- trades a few more sorts for fewer trips through the slow path.
+// `room`: compact once a buffer holds more than this many candidates (set by the host, 32*E - 8).  Between
+// compactions the threshold is stale (it admits rows that the next sort throws away again); compacting earlier
+// was measured and is slower, because every sort stalls the warp on L2 round trips (cvdb_api.cu).
 template <int E, bool strict_own = true>
 __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room) {
     unsigned mask = __ballot_sync(0xffffffffu, st.cnt > room);
