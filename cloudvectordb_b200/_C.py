@@ -43,6 +43,8 @@ SIGNATURES = {
     "cvdb_index_destroy": (C.c_int, [C.c_void_p]),
     "cvdb_index_reset": (C.c_int, [C.c_void_p]),
     "cvdb_index_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
+    "cvdb_index_truncate": (C.c_int, [C.c_void_p, C.c_int64]),
+    "cvdb_index_nonfinite_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "cvdb_index_ntotal": (C.c_int64, [C.c_void_p]),
     "cvdb_index_dim": (C.c_int, [C.c_void_p]),
     "cvdb_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
@@ -71,6 +73,7 @@ SIGNATURES = {
     "cvdb_kmeans_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
     "cvdb_kmeans_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cvdb_kmeans_split_empty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "cvdb_last_error": (C.c_char_p, []),
     "cvdb_kernel_launches": (C.c_int64, []),
     "cvdb_version": (C.c_int, []),

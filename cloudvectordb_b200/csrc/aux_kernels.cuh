@@ -39,7 +39,7 @@ __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename Tin>
 __global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, int64_t in_stride,
                                  __nv_bfloat16* __restrict__ out, int Kp, int planes, int l2, int is_query,
-                                 float* __restrict__ norms) {
+                                 float* __restrict__ norms, unsigned long long* __restrict__ bad_rows) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -70,6 +70,8 @@ __global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, i
         nrm = warp_sum(nrm);
         if (lane == 0) {
             if (norms) norms[r] = nrm;
+            // a NaN or infinite element makes the squared norm non-finite: count such rows (cvdb_index_nonfinite_rows)
+            if (bad_rows && !isfinite(nrm)) atomicAdd(bad_rows, 1ull);
             if (l2) {
                 if (is_query) {
                     const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
@@ -236,6 +238,67 @@ __global__ void kmeans_finalize_kernel(const float* __restrict__ sums, const int
     if (i >= static_cast<int64_t>(K) * d) return;
     const int c = counts[i / d];
     if (c > 0) centroids[i] = sums[i] / static_cast<float>(c);
+}
+
+// Empty clusters after an update (FAISS convention: an empty cluster takes half of a big one).  One block walks the
+// empty clusters in ascending order; each takes the currently largest cluster j (ties -> lower id, at least two
+// points), copies its centroid with a symmetric relative perturbation of eps (even dimensions up / odd down, the
+// donor the other way round) and half of its count.  Deterministic, so every rank of a sharded run -- which sees
+// the same all-reduced counts -- does the same thing.  n_split (optional) receives the number of clusters re-seeded.
+__global__ void __launch_bounds__(1024, 1)
+kmeans_split_empty_kernel(float* __restrict__ centroids, int32_t* __restrict__ counts, int K, int d, float eps,
+                          int32_t* __restrict__ n_split) {
+    __shared__ unsigned long long s_key[32];
+    __shared__ unsigned char s_flag[1024];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int done = 0, split = 0;
+    for (int base = 0; base < K && !done; base += 1024) {
+        const int idx = base + tid;
+        const int empty = idx < K && counts[idx] == 0;
+        if (!__syncthreads_or(empty)) continue;
+        s_flag[tid] = static_cast<unsigned char>(empty);
+        __syncthreads();
+        for (int i = 0; i < 1024 && !done; ++i) {
+            if (!s_flag[i]) continue;  // uniform
+            const int e = base + i;
+            // block-wide argmax of counts, ties -> lower id
+            unsigned long long best = 0;
+            for (int j = tid; j < K; j += 1024) {
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(static_cast<uint32_t>(counts[j])) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(j));
+                best = key > best ? key : best;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane == 0) s_key[warp] = best;
+            __syncthreads();
+            best = s_key[0];
+            for (int w = 1; w < 32; ++w) best = s_key[w] > best ? s_key[w] : best;
+            const int cj = static_cast<int>(best >> 32);
+            const int j = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(best & 0xFFFFFFFFu));
+            if (cj < 2) {
+                done = 1;  // nothing left to split (uniform: every thread computed the same key)
+            } else {
+                for (int c = tid; c < d; c += 1024) {
+                    const float v = centroids[static_cast<size_t>(j) * d + c];
+                    const float up = v * (1.f + eps), down = v * (1.f - eps);
+                    centroids[static_cast<size_t>(e) * d + c] = (c & 1) ? down : up;
+                    centroids[static_cast<size_t>(j) * d + c] = (c & 1) ? up : down;
+                }
+                if (tid == 0) {
+                    counts[e] = cj / 2;
+                    counts[j] = cj - cj / 2;
+                }
+                ++split;
+            }
+            __syncthreads();  // counts / centroids / s_key settled before the next argmax
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && n_split != nullptr) *n_split = split;
 }
 
 // ---------------------------------------------------------------------------

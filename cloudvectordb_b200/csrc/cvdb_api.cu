@@ -149,6 +149,7 @@ struct Index {
     DevBuf row_ids, list_off, ivf_cnt, ivf_pair_off, ivf_item_off, ivf_cursor, ivf_scal, ivf_items, ivf_pair_query,
         ivf_pair_dst, ivf_qg, ivf_probes;
     DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
+    DevBuf bad_rows;  // one uint64: rows (added or queried) whose squared norm was not finite
     bool has_groups = false;
 
     // ring of event pairs bracketing profiled GEMM+top-k launches (opts.profile)
@@ -202,7 +203,8 @@ void launch_pack(const Tin* in, int64_t n, int d, __nv_bfloat16* out, const Inde
     const int threads = 256;
     const int64_t blocks = std::min<int64_t>(ceil_div(n, threads / 32), 148 * 32);
     pack_rows_kernel<Tin><<<static_cast<unsigned>(blocks), threads, 0, st>>>(in, n, d, d, out, ix->Kp, ix->planes,
-                                                                                ix->metric == CVDB_METRIC_L2, is_query, norms);
+                                                                                ix->metric == CVDB_METRIC_L2, is_query, norms,
+                                                                                static_cast<unsigned long long*>(ix->bad_rows.p));
     ++g_launches;
 }
 
@@ -598,6 +600,15 @@ int cvdb_index_create(int d, int metric, int storage, int device, cvdb_index_t* 
     ix->Kp = pad64 ? round_up(ix->Kd, 64) : round_up(ix->Kd, 8);
     ix->row_elems = ix->planes * ix->Kp;
     ix->num_sms = prop.multiProcessorCount;
+    {
+        cvdb_guard g(device);
+        if (ix->bad_rows.ensure(8) != CVDB_OK || cudaMemset(ix->bad_rows.p, 0, 8) != cudaSuccess ||
+            cudaStreamSynchronize(nullptr) != cudaSuccess) {
+            ix->bad_rows.release();
+            delete ix;
+            return fail(CVDB_ENOMEM, "cudaMalloc for the index state failed");
+        }
+    }
     *out = reinterpret_cast<cvdb_index_t>(ix);
     return CVDB_OK;
 }
@@ -612,7 +623,7 @@ int cvdb_index_destroy(cvdb_index_t h) {
                       &ix->ivf_scal, &ix->ivf_items, &ix->ivf_pair_query, &ix->ivf_pair_dst, &ix->ivf_qg, &ix->ivf_probes})
         b->release();
     for (DevBuf* b : {&ix->gthr, &ix->waves, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
-                      &ix->ids_b, &ix->groups})
+                      &ix->ids_b, &ix->groups, &ix->bad_rows})
         b->release();
     for (int i = 0; i < Index::kProfSlots; ++i) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
@@ -629,6 +640,31 @@ int cvdb_index_reset(cvdb_index_t h) {
     ix->has_groups = false;
     ix->grouped = false;
     ix->row_ids_n = 0;
+    return CVDB_OK;
+}
+
+int cvdb_index_truncate(cvdb_index_t h, int64_t n) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (n < 0 || n > ix->ntotal)
+        return fail(CVDB_EINVAL, "truncate to %lld rows: the index holds %lld", static_cast<long long>(n),
+                    static_cast<long long>(ix->ntotal));
+    if (ix->grouped && n != ix->ntotal)
+        return fail(CVDB_EINVAL, "rows are stored list-major after cvdb_index_group_by_list; the last rows added are not the last rows stored");
+    ix->ntotal = n;
+    return CVDB_OK;
+}
+
+int cvdb_index_nonfinite_rows(cvdb_index_t h, int64_t* count_out, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!count_out) return fail(CVDB_EINVAL, "count_out is null");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long v = 0;
+    CU_TRY(cudaMemcpyAsync(&v, ix->bad_rows.p, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *count_out = static_cast<int64_t>(v);
     return CVDB_OK;
 }
 
@@ -1069,6 +1105,17 @@ int cvdb_kmeans_finalize(const float* sums, const int32_t* counts, int K, int d,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t total = static_cast<int64_t>(K) * d;
     kmeans_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, st>>>(sums, counts, K, d, centroids);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+int cvdb_kmeans_split_empty(float* centroids, int32_t* counts, int K, int d, float eps, int32_t* n_split, void* stream) {
+    if (K < 1 || d < 1) return fail(CVDB_EINVAL, "bad sizes");
+    if (!centroids || !counts) return fail(CVDB_EINVAL, "null pointer");
+    if (!(eps >= 0.f && eps < 1.f)) return fail(CVDB_EINVAL, "eps must be in [0, 1)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    kmeans_split_empty_kernel<<<1, 1024, 0, st>>>(centroids, counts, K, d, eps, n_split);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return CVDB_OK;

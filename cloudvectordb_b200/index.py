@@ -128,10 +128,31 @@ class IndexFlat:
     def reserve(self, n: int) -> None:
         _C.check(_C.lib().cvdb_index_reserve(self._h, int(n)))
 
-    def add(self, x) -> None:
+    def truncate(self, n: int) -> None:
+        """Drop the rows added last so that ``ntotal == n`` (keeps the allocation)."""
+        _C.check(_C.lib().cvdb_index_truncate(self._h, int(n)))
+
+    def nonfinite_rows(self, stream=None) -> int:
+        """Rows seen so far (added or queried) that held a NaN / infinite element; waits for ``stream``."""
+        out = C.c_int64(0)
+        _C.check(_C.lib().cvdb_index_nonfinite_rows(self._h, C.byref(out), stream))
+        return int(out.value)
+
+    def add(self, x, check_finite: bool = False) -> None:
+        """Append rows.  ``check_finite=True`` rejects the whole batch (ValueError, index unchanged) if any row
+        holds a NaN or infinite value; the check is a counter kept by the packing kernel, it costs one
+        stream synchronisation and no extra pass over the data."""
         b = _Buf(x, self._d, "x")
         self._check_place(b)
-        _C.check(_C.lib().cvdb_index_add(self._h, b.ptr, b.n, b.dtype, int(b.on_device), _stream_for(b)))
+        st = _stream_for(b)
+        if check_finite:
+            n0, bad0 = self.ntotal, self.nonfinite_rows(st)
+        _C.check(_C.lib().cvdb_index_add(self._h, b.ptr, b.n, b.dtype, int(b.on_device), st))
+        if check_finite:
+            bad = self.nonfinite_rows(st) - bad0
+            if bad:
+                self.truncate(n0)
+                raise ValueError(f"add(): {bad} of {b.n} rows hold NaN or infinite values; nothing was added")
 
     def set_groups(self, group_db) -> None:
         """Group id per database row; search(..., group_q=) drops same-group rows."""
@@ -154,10 +175,12 @@ class IndexFlat:
         _C.check(_C.lib().cvdb_index_set_groups(self._h, a.ctypes.data, 0, None))
 
     def search(self, q, k: int, *, self_ids=None, group_q=None, id_base: int = 0, profile: bool = False,
-               force_slices: int = 0, force_variant: int = 0, debug_flags: int = 0) -> Tuple[object, object]:
+               force_slices: int = 0, force_variant: int = 0, debug_flags: int = 0,
+               check_finite: bool = False) -> Tuple[object, object]:
         b = _Buf(q, self._d, "q")
         self._check_place(b)
         k = int(k)
+        bad0 = self.nonfinite_rows(_stream_for(b)) if check_finite else 0
         opts = _C.SearchOpts()
         sp, keep_s = _i32_buf(self_ids, b.n, b, "self_ids")
         gp, keep_g = _i32_buf(group_q, b.n, b, "group_q")
@@ -180,6 +203,10 @@ class IndexFlat:
         _C.check(_C.lib().cvdb_index_search(self._h, b.ptr, b.n, b.dtype, k, dp, ip, int(b.on_device), C.byref(opts),
                                             _stream_for(b)))
         del keep_s, keep_g
+        if check_finite:
+            bad = self.nonfinite_rows(_stream_for(b)) - bad0
+            if bad:
+                raise ValueError(f"search(): {bad} of {b.n} queries hold NaN or infinite values")
         if b.on_device:
             return D, I
         if b.kind == "torch":

@@ -4,7 +4,10 @@ are the index rows, the points are the queries) and whose update step is a
 scatter-add kernel, all-reduced across ranks when torch.distributed is up.
 
 FAISS ``Kmeans(d, k, niter, seed)`` shape: ``train(x)``, ``centroids``,
-``assign(x)``, ``obj``.  Empty clusters keep their previous centroid.
+``assign(x)``, ``obj``.  Empty clusters take half of the largest cluster (FAISS
+splits a big cluster too; here the donor is the largest one, so that every rank
+of a sharded run re-seeds identically); ``split_empty=False`` keeps the previous
+centroid instead.
 """
 from __future__ import annotations
 
@@ -20,11 +23,13 @@ from .index import IndexFlat
 
 class Kmeans:
     def __init__(self, d: int, k: int, niter: int = 10, seed: int = 42, storage: str = "bf16",
-                 device: Optional[int] = None, group=None):
+                 device: Optional[int] = None, group=None, split_empty: bool = True, split_eps: float = 1.0 / 1024):
         self.d, self.k, self.niter, self.seed = int(d), int(k), int(niter), int(seed)
         self.storage = storage
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.group = group
+        self.split_empty, self.split_eps = bool(split_empty), float(split_eps)
+        self.last_nsplit: Optional[torch.Tensor] = None   # device int32: clusters re-seeded by the last step
         self.centroids: Optional[torch.Tensor] = None
         self.obj = []
         self._index: Optional[IndexFlat] = None
@@ -81,6 +86,10 @@ class Kmeans:
             dist.all_reduce(obj, group=self.group)
         _C.check(lib.cvdb_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), self.k, self.d,
                                           self.centroids.data_ptr(), stream))
+        if self.split_empty:
+            self.last_nsplit = torch.zeros((1,), dtype=torch.int32, device=x.device)
+            _C.check(lib.cvdb_kmeans_split_empty(self.centroids.data_ptr(), counts.data_ptr(), self.k, self.d,
+                                                 self.split_eps, self.last_nsplit.data_ptr(), stream))
         if profile:
             ev[3].record()
             torch.cuda.synchronize(self.device)

@@ -69,7 +69,9 @@ typedef struct cvdb_search_opts {
     int force_variant;       /* 0: auto; 1..4: force that kernel variant (cvdb_index_last_variant)   */
     int debug_flags;         /* kernel-tuning experiments only (results become invalid): 1 = skip the
                                 top-k scan, 2 = skip the TMEM read as well, 4 = no threshold sharing between slices,
-                                8 = no wave alignment of the producers */
+                                8 = no wave alignment of the producers, 16 = run all K-steps of the padded row width,
+                                32 = always sort the whole candidate buffer at the end of a work item
+                                (4, 8, 16 and 32 leave the results valid) */
 } cvdb_search_opts;
 
 /* -- index lifetime -------------------------------------------------------
@@ -78,11 +80,19 @@ int cvdb_index_create(int d, int metric, int storage, int device, cvdb_index_t* 
 int cvdb_index_destroy(cvdb_index_t idx);
 int cvdb_index_reset(cvdb_index_t idx);               /* ntotal = 0, keeps the allocation   */
 int cvdb_index_reserve(cvdb_index_t idx, int64_t n);  /* capacity for n rows in total       */
+int cvdb_index_truncate(cvdb_index_t idx, int64_t n); /* drop the rows added last: ntotal = n <= ntotal (flat layout only) */
 int64_t cvdb_index_ntotal(cvdb_index_t idx);
 int cvdb_index_dim(cvdb_index_t idx);
 
 /* FAISS add(x): append n rows (copied; caller keeps ownership of x). */
 int cvdb_index_add(cvdb_index_t idx, const void* x, int64_t n, int dtype, int on_device, void* stream);
+
+/* Input validation without a hidden synchronisation on the hot path (SURVEY.md 4.2 "NaN/Inf rejection"): the
+ * kernel that packs rows -- database rows in add(), query rows in search()/assign() -- counts the rows whose
+ * squared norm is not finite (a NaN or infinite element, or values too large for bf16).  This call waits for
+ * `stream` and returns the running total since cvdb_index_create.  A caller that wants to reject such input
+ * compares the total before and after a call and undoes an add() with cvdb_index_truncate. */
+int cvdb_index_nonfinite_rows(cvdb_index_t idx, int64_t* count_out, void* stream);
 
 /* Group id per database row [ntotal] for positive exclusion in hard-negative
  * mining (README.md:2 "dataset of triplets"); NULL clears. */
@@ -150,6 +160,12 @@ int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int
                            int32_t* counts, void* stream);
 /* centroids[j] = sums[j] / counts[j] where counts[j] > 0 (else unchanged).  Device pointers only. */
 int cvdb_kmeans_finalize(const float* sums, const int32_t* counts, int K, int d, float* centroids, void* stream);
+/* Re-seed empty clusters after finalize (FAISS Kmeans convention: an empty cluster takes half of a big one).  In
+ * ascending order every cluster with counts == 0 takes the currently largest cluster j (ties -> lower id; stops when
+ * it has fewer than 2 points): centroid[e] = centroid[j] * (1 +- eps) alternating by dimension, centroid[j] the other
+ * way round, counts[e] = counts[j] / 2, counts[j] -= counts[e].  Deterministic, so ranks holding the same all-reduced
+ * counts agree.  n_split (device pointer, may be NULL) receives the number of clusters re-seeded.  Device pointers. */
+int cvdb_kmeans_split_empty(float* centroids, int32_t* counts, int K, int d, float eps, int32_t* n_split, void* stream);
 
 /* -- host-side planning (no GPU needed; exposed for tests) -----------------------------------------
  * How a search splits the database: work item = (query tile, database slice).  Given the number of query tiles,

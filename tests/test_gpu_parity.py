@@ -377,6 +377,53 @@ def test_kmeans_bf16_assign_and_update_large():
     assert all(b <= a * (1 + 1e-5) for a, b in zip(km2.obj, km2.obj[1:]))
 
 
+@pytest.mark.parametrize("K,d,n_empty", [(16, 8, 3), (1500, 100, 200), (70000, 32, 5000), (64, 384, 63), (5, 3, 0)])
+def test_kmeans_split_empty_matches_oracle(K, d, n_empty):
+    """cvdb_kmeans_split_empty against the oracle restatement: bit-exact centroids, counts and split count."""
+    from cloudvectordb_b200 import _C
+    rng = np.random.default_rng(K + d)
+    cent = rng.standard_normal((K, d)).astype(np.float32)
+    counts = rng.integers(1, 50, K).astype(np.int32)
+    counts[rng.integers(0, K, 5)] = 49                       # ties for the largest cluster
+    counts[rng.choice(K, n_empty, replace=False)] = 0
+    if K == 64:
+        counts[counts > 0] = 40                              # a single donor is split again and again, then runs dry
+    c_ref, n_ref, s_ref = O.kmeans_split_empty_ref(cent, counts)
+    ct, nt = torch.from_numpy(cent).cuda(), torch.from_numpy(counts).cuda()
+    ns = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    _C.check(_C.lib().cvdb_kmeans_split_empty(ct.data_ptr(), nt.data_ptr(), K, d, 1.0 / 1024, ns.data_ptr(),
+                                              int(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert int(ns.item()) == s_ref
+    assert np.array_equal(nt.cpu().numpy().astype(np.int64), n_ref)
+    assert np.array_equal(ct.cpu().numpy(), c_ref)
+
+
+def test_kmeans_reseeds_empty_clusters():
+    """Two identical initial centroids leave one cluster empty after the first assignment (ties go to the lower
+    id); with split_empty it is re-seeded from the largest cluster, without it the old centroid stays."""
+    from cloudvectordb_b200 import Kmeans
+    rng = np.random.default_rng(8)
+    n, d, K = 4000, 32, 8
+    x = O.bf16_round(unit_rows(rng, n, d))
+    init = x[:K].copy()
+    init[5] = init[2]
+    for split in (True, False):
+        km = Kmeans(d, K, niter=1, storage="exact", device=0, split_empty=split)
+        km.train(x, init_centroids=init)
+        a_ref, _ = O.kmeans_assign_ref(x, init)
+        newc, counts, _ = O.kmeans_update_ref(x, a_ref, init)
+        assert counts[5] == 0
+        if split:
+            newc, counts, s = O.kmeans_split_empty_ref(newc, counts)
+            assert s == 1 and int(km.last_nsplit.item()) == 1
+        assert np.array_equal(km.last_counts.cpu().numpy().astype(np.int64), counts)
+        assert np.allclose(km.centroids.cpu().numpy(), newc, rtol=1e-4, atol=1e-6)
+    km = Kmeans(d, K, niter=6, storage="exact", device=0)
+    km.train(x, init_centroids=init)
+    assert int((km.last_counts > 0).sum().item()) == K          # no cluster stays empty
+
+
 # ---- full-size properties (sizes the oracle cannot reach) ----------------------------------
 def test_large_database_properties():
     """2M x 768 bf16: planted neighbours are found, results are sorted, a
@@ -495,6 +542,51 @@ def test_errors_are_reported_not_swallowed():
         idx.search(np.ones((2, 8), np.float32), 3)
     with pytest.raises(_C.CvdbError):
         idx.search(np.ones((2, 16), np.float32), 3, group_q=np.zeros(2, np.int32))   # no groups set
+    idx.close()
+
+
+@pytest.mark.parametrize("storage", ["bf16", "exact"])
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_nonfinite_rows_are_counted_and_rejected_on_request(metric, storage):
+    """SURVEY.md 4.2 adversarial row "NaN/Inf rejection": add()/search() with check_finite=True raise and leave the
+    index as it was; without it the rows are counted (cvdb_index_nonfinite_rows) and nothing else changes."""
+    rng = np.random.default_rng(77)
+    d, k = 72, 5
+    xb = O.bf16_round(unit_rows(rng, 700, d))
+    xq = O.bf16_round(unit_rows(rng, 40, d))
+    idx = make_index(d, metric, storage)
+    idx.add(xb[:500], check_finite=True)
+    assert idx.ntotal == 500 and idx.nonfinite_rows() == 0
+    bad = xb[500:].copy()
+    bad[3, 7] = np.nan
+    bad[90, 0] = np.inf
+    bad[91, d - 1] = -np.inf
+    with pytest.raises(ValueError, match="3 of 200 rows"):
+        idx.add(bad, check_finite=True)
+    assert idx.ntotal == 500 and idx.nonfinite_rows() == 3
+    with pytest.raises(ValueError, match="3 of 200 rows"):                    # same from device memory
+        idx.add(torch.from_numpy(bad).cuda(), check_finite=True)
+    assert idx.ntotal == 500 and idx.nonfinite_rows() == 6
+    idx.add(xb[500:], check_finite=True)                                      # the clean batch goes in
+    D, I = idx.search(xq, k, check_finite=True)
+    D_ref, I_ref = O.search_ref(xb, xq, k, M[metric])
+    assert_parity(D, I, D_ref, I_ref, metric, tie_tol=2e-5)
+    qbad = xq.copy()
+    qbad[11, 5] = np.nan
+    with pytest.raises(ValueError, match="1 of 40 queries"):
+        idx.search(qbad, k, check_finite=True)
+    D2, I2 = idx.search(qbad, k)                                              # unchecked: other queries unaffected
+    keep = np.arange(40) != 11
+    assert np.array_equal(I2[keep], I[keep]) and np.array_equal(D2[keep], D[keep])
+    assert idx.nonfinite_rows() == 8
+    idx.truncate(600)
+    assert idx.ntotal == 600
+    D3, I3 = idx.search(xq, k)
+    D_ref3, I_ref3 = O.search_ref(xb[:600], xq, k, M[metric])
+    assert_parity(D3, I3, D_ref3, I_ref3, metric, tie_tol=2e-5)
+    from cloudvectordb_b200 import _C
+    with pytest.raises(_C.CvdbError):
+        idx.truncate(601)
     idx.close()
 
 

@@ -202,3 +202,27 @@ def test_triplet_oracle_rules():
     assert T[0].tolist() == [[10, 6, 7], [10, 6, 8]]     # 5 is above the limit, 6 is the positive itself
     assert T[1].tolist() == [[11, 3, 9], [-1, -1, -1]]   # list ends at the first -1
     assert (T[2] == -1).all()                            # no positive -> no triplet
+
+
+def test_kmeans_split_empty_ref_properties():
+    """Empty clusters take half of the largest cluster; totals are conserved; order and tie rule are fixed."""
+    rng = np.random.default_rng(5)
+    K, d = 12, 6
+    cent = rng.standard_normal((K, d)).astype(np.float32)
+    counts = np.array([7, 0, 3, 9, 0, 9, 1, 0, 2, 2, 0, 5])
+    c2, n2, n_split = O.kmeans_split_empty_ref(cent, counts, eps=1.0 / 1024)
+    assert n_split == 4 and n2.sum() == counts.sum() and (n2 > 0).all()
+    # cluster 1 takes half of cluster 3 (9 = first maximum): 4 / 5; cluster 4 then takes half of cluster 5 (9)
+    assert n2[1] == 4 and n2[4] == 4 and n2[3] in (5, 2, 3) and n2[5] in (5, 2, 3)
+    up, down = np.float32(1 + 1 / 1024), np.float32(1 - 1 / 1024)
+    # cluster 7 takes half of cluster 0 (7 is the largest left): check the perturbation pattern on an untouched donor
+    assert np.array_equal(c2[7][0::2], cent[0][0::2] * up) and np.array_equal(c2[7][1::2], cent[0][1::2] * down)
+    assert np.array_equal(c2[0][0::2], cent[0][0::2] * down) and np.array_equal(c2[0][1::2], cent[0][1::2] * up)
+    untouched = [2, 6, 8, 9, 11]
+    assert np.array_equal(c2[untouched], cent[untouched]) and np.array_equal(n2[untouched], counts[untouched])
+    # nothing to split from: all donors have < 2 points
+    c3, n3, s3 = O.kmeans_split_empty_ref(cent, np.array([1, 0, 1, 0] + [1] * 8))
+    assert s3 == 0 and np.array_equal(c3, cent)
+    # no empties: identity
+    c4, n4, s4 = O.kmeans_split_empty_ref(cent, np.arange(1, K + 1))
+    assert s4 == 0 and np.array_equal(c4, cent) and np.array_equal(n4, np.arange(1, K + 1))
