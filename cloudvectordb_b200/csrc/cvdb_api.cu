@@ -243,14 +243,15 @@ int pick_E(int k) {
     return 128;
 }
 
-// Candidates a buffer of C slots may hold before it is compacted: C - 8 (eight free slots are needed before
-// each group of eight scores).  CVDB_ROOM_EXTRA = x lowers it to k + x (experiments only).
+// Candidates a buffer of C slots may hold before it is compacted.  The scan makes room once per group of eight
+// scores (32-slot buffers, k <= 12) or once per chunk of 32 scores (larger buffers), so that many slots must stay
+// free.  CVDB_ROOM_EXTRA = x lowers the trigger to k + x (experiments only).
 int compaction_trigger(int k, int C) {
-    if (C > 512) return C - 8;  // in-memory sorts (k > 248) are expensive: compact as rarely as possible
     // measured (mining shape, k = 50): compacting earlier than necessary is slower (500 / 524 / 550 ms for
     // C-8 / k+25 / k+12) -- a compaction stalls the warp on L2 round trips -- so fill the buffer.
-    int room = C - 8;
-    if (const char* env = getenv("CVDB_ROOM_EXTRA")) room = std::min(C - 8, k + std::max(1, atoi(env)));
+    const int full = C == 32 ? C - 8 : C - 32;
+    int room = full;
+    if (const char* env = getenv("CVDB_ROOM_EXTRA")) room = std::min(full, k + std::max(1, atoi(env)));
     return room;
 }
 

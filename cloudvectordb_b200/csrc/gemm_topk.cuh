@@ -152,7 +152,8 @@ __device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k) {
     return __ldcg(reinterpret_cast<const unsigned long long*>(b + k - 1));
 }
 
-// `room`: compact once a buffer holds more than this many candidates (set by the host, 32*E - 8).  Between
+// `room`: compact once a buffer holds more than this many candidates (set by the host: 32*E - 8 for E = 1,
+// 32*E - 32 otherwise, see scan_chunk).  Between
 // compactions the threshold is stale (it admits rows that the next sort throws away again); compacting earlier
 // was measured and is slower, because every sort stalls the warp on L2 round trips (cvdb_api.cu).
 template <int E, bool strict_own = true>
@@ -196,23 +197,46 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
     }
     const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
     if (!__any_sync(0xffffffffu, m > st.thr)) return;  // common case once the threshold has settled
+    if constexpr (E >= 2) {
+        // Buffers of 64+ slots: make room for a whole chunk (32 candidates) once, then let only the lanes that
+        // hold a candidate walk their groups -- typically a single lane with a single row, so the divergent
+        // walk costs one pass instead of a warp-wide pass per group of eight.
+        make_room<E>(st, k, room);
+        if (m > st.thr) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
-        if constexpr (E > 0) make_room<E>(st, k, room);
+            for (int g = 0; g < 4; ++g) {
+                if (!(m8[g] > st.thr)) continue;
 #pragma unroll
-        for (int j = 8 * g; j < 8 * g + 8; ++j) {
-            const float s = __uint_as_float(v[j]);
-            if (s > st.thr) {
-                const uint32_t row = row0 + j;
-                bool ok = row < row_end && row != self;
-                if (ok && grp >= 0 && group_db != nullptr) ok = __ldg(group_db + row) != grp;
-                if (ok) {
-                    if constexpr (E > 0) {
-                        st.buf[st.cnt++] = make_key(s, row);
-                    } else {
-                        st.best = make_key(s, row);
-                        st.thr = s;
+                for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                    const float s = __uint_as_float(v[j]);
+                    if (s > st.thr) {
+                        const uint32_t row = row0 + j;
+                        bool ok = row < row_end && row != self;
+                        if (ok && grp >= 0 && group_db != nullptr) ok = __ldg(group_db + row) != grp;
+                        if (ok) st.buf[st.cnt++] = make_key(s, row);
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
+            if constexpr (E > 0) make_room<E>(st, k, room);
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                const float s = __uint_as_float(v[j]);
+                if (s > st.thr) {
+                    const uint32_t row = row0 + j;
+                    bool ok = row < row_end && row != self;
+                    if (ok && grp >= 0 && group_db != nullptr) ok = __ldg(group_db + row) != grp;
+                    if (ok) {
+                        if constexpr (E > 0) {
+                            st.buf[st.cnt++] = make_key(s, row);
+                        } else {
+                            st.best = make_key(s, row);
+                            st.thr = s;
+                        }
                     }
                 }
             }
@@ -237,6 +261,24 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
     }
 }
 
+// A buffer whose candidates all sit in its first 32*ES slots: sort only those (warp-cooperative) and write the k
+// output entries.  Returns the k-th best key (0 when fewer than k candidates exist).
+template <int ES>
+__device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* out, int k) {
+    const int lane = threadIdx.x & 31;
+    uint64_t key[ES];
+#pragma unroll
+    for (int e = 0; e < ES; ++e) key[e] = __ldcg(reinterpret_cast<const unsigned long long*>(b + e * 32 + lane));
+    warp_bitonic_sort_desc<ES>(key);
+#pragma unroll
+    for (int e = 0; e < ES; ++e) {
+        const int pos = e * 32 + lane;
+        if (pos < k) out[pos] = key[e];
+    }
+    for (int pos = 32 * ES + lane; pos < k; pos += 32) out[pos] = 0;
+    return k <= 32 * ES ? warp_sorted_at<ES>(key, k - 1) : 0;
+}
+
 // End of a work item: sorted top-k of every query of the warp -> part[q][slice][0..k).
 template <int E>
 __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams& p, int q_base, int q_row, bool q_valid,
@@ -252,14 +294,16 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
             uint64_t kth;
             if constexpr (E <= 16) {
                 // Later slices start from a good shared threshold and often collect only a handful of rows: sort
-                // just the first 32 slots then (a 5x cheaper network than the 128-slot one of k = 50).
-                if (E > 1 && __shfl_sync(0xffffffffu, st.cnt, l) <= 32 && !(p.dbg & 32)) {
-                    uint64_t key1[1];
-                    key1[0] = __ldcg(reinterpret_cast<const unsigned long long*>(b + lane));
-                    warp_bitonic_sort_desc<1>(key1);
-                    kth = p.k <= 32 ? warp_sorted_at<1>(key1, p.k - 1) : 0;
-                    if (static_cast<int>(lane) < p.k) out[lane] = key1[0];
-                    for (int pos = 32 + lane; pos < p.k; pos += 32) out[pos] = 0;
+                // just the filled prefix then (32 slots cost a fifth of the 128-slot network of k = 50).
+                const int cnt_l = (p.dbg & 32) ? 32 * E : __shfl_sync(0xffffffffu, st.cnt, l);
+                if (E > 1 && cnt_l <= 32) {
+                    kth = flush_prefix<1>(b, out, p.k);
+                } else if (E > 2 && cnt_l <= 64) {
+                    kth = flush_prefix<2>(b, out, p.k);
+                } else if (E > 4 && cnt_l <= 128) {
+                    kth = flush_prefix<4>(b, out, p.k);
+                } else if (E > 8 && cnt_l <= 256) {
+                    kth = flush_prefix<8>(b, out, p.k);
                 } else {
                     uint64_t key[E];
                     kth = warp_compact<E>(b, p.k, key);
