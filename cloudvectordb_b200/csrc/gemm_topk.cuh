@@ -75,6 +75,7 @@ struct LaneTopk {
     int cnt;         // filled slots in buf
     uint64_t* buf;   // 32*E slots, slot p of every query of the warp is zero when p >= cnt
     uint32_t* gq;    // &gthr[query] (null for padding rows)
+    int grp = -1;    // group id of the query when same-group rows are excluded (checked when the buffer is sorted)
 };
 template <>
 struct LaneTopk<0> {
@@ -104,13 +105,30 @@ __device__ __forceinline__ float publish_and_refresh(uint32_t* gq, uint64_t kth,
     return fmaxf(thr, t);
 }
 
+// Group exclusion (hard-negative mining: rows of the query's own group are not candidates).  Looking the group of
+// a row up while scanning would put an L2 round trip into the per-candidate path, so rows are collected
+// unchecked and the check runs here, on the whole buffer at once (the loads overlap), right before every sort;
+// thresholds only ever come out of a sort, so an unchecked row never influences one.  grp < 0: nothing to do.
+template <int E>
+__device__ __forceinline__ void drop_same_group(uint64_t (&key)[E], int grp, const int32_t* __restrict__ group_db) {
+    if (grp < 0 || group_db == nullptr) return;  // warp-uniform
+    int g[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) g[e] = key[e] != 0 ? __ldg(group_db + key_row(key[e])) : -1;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (g[e] == grp) key[e] = 0;
+}
+
 // Sort the buffer of lane `l` (warp-cooperative), keep its best k, zero the rest.
 // Returns the k-th best key (0 when fewer than k candidates exist).
 template <int E>
-__device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&key)[E]) {
+__device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&key)[E], int grp = -1,
+                                                 const int32_t* __restrict__ group_db = nullptr) {
     const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
     for (int e = 0; e < E; ++e) key[e] = __ldcg(reinterpret_cast<const unsigned long long*>(b + e * 32 + lane));
+    drop_same_group<E>(key, grp, group_db);
     warp_bitonic_sort_desc<E>(key);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -126,10 +144,18 @@ __device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&
 // not fit the register file (and takes minutes to compile).  Slower per sort, but these buffers are sized >= 2k so
 // sorts are rare.  Returns the k-th best key; leaves the best k sorted at the front and zeros behind them.
 template <int E>
-__device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k) {
+__device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k, int grp = -1,
+                                                  const int32_t* __restrict__ group_db = nullptr) {
     constexpr int C = 32 * E;
     const int lane = threadIdx.x & 31;
     __syncwarp();
+    if (grp >= 0 && group_db != nullptr) {  // see drop_same_group
+        for (int t = lane; t < C; t += 32) {
+            const uint64_t a = __ldcg(reinterpret_cast<const unsigned long long*>(b + t));
+            if (a != 0 && __ldg(group_db + key_row(a)) == grp) b[t] = 0;
+        }
+        __syncwarp();
+    }
     for (int size = 2; size <= C; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             const int sh = __ffs(stride) - 1;
@@ -157,7 +183,7 @@ __device__ __noinline__ uint64_t warp_compact_mem(uint64_t* b, int k) {
 // compactions the threshold is stale (it admits rows that the next sort throws away again); compacting earlier
 // was measured and is slower, because every sort stalls the warp on L2 round trips (cvdb_api.cu).
 template <int E, bool strict_own = true>
-__device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room) {
+__device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room, const int32_t* __restrict__ group_db = nullptr) {
     unsigned mask = __ballot_sync(0xffffffffu, st.cnt > room);
     if (mask == 0) return;
     __syncwarp();
@@ -166,12 +192,13 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room) {
         const int l = __ffs(mask) - 1;
         mask &= mask - 1;
         uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
+        const int grp_l = __shfl_sync(0xffffffffu, st.grp, l);
         uint64_t kth;
         if constexpr (E <= 16) {
             uint64_t key[E];
-            kth = warp_compact<E>(b, k, key);
+            kth = warp_compact<E>(b, k, key, grp_l, group_db);
         } else {
-            kth = warp_compact_mem<E>(b, k);
+            kth = warp_compact_mem<E>(b, k, grp_l, group_db);
         }
         if (static_cast<int>(lane) == l) {
             st.thr = publish_and_refresh<strict_own>(st.gq, kth, st.thr);
@@ -201,7 +228,7 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
         // Buffers of 64+ slots: make room for a whole chunk (32 candidates) once, then let only the lanes that
         // hold a candidate walk their groups -- typically a single lane with a single row, so the divergent
         // walk costs one pass instead of a warp-wide pass per group of eight.
-        make_room<E>(st, k, room);
+        make_room<E>(st, k, room, group_db);
         if (m > st.thr) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -211,9 +238,7 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
                     const float s = __uint_as_float(v[j]);
                     if (s > st.thr) {
                         const uint32_t row = row0 + j;
-                        bool ok = row < row_end && row != self;
-                        if (ok && grp >= 0 && group_db != nullptr) ok = __ldg(group_db + row) != grp;
-                        if (ok) st.buf[st.cnt++] = make_key(s, row);
+                        if (row < row_end && row != self) st.buf[st.cnt++] = make_key(s, row);  // group: see drop_same_group
                     }
                 }
             }
@@ -222,14 +247,15 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
-            if constexpr (E > 0) make_room<E>(st, k, room);
+            if constexpr (E > 0) make_room<E>(st, k, room, group_db);
 #pragma unroll
             for (int j = 8 * g; j < 8 * g + 8; ++j) {
                 const float s = __uint_as_float(v[j]);
                 if (s > st.thr) {
                     const uint32_t row = row0 + j;
                     bool ok = row < row_end && row != self;
-                    if (ok && grp >= 0 && group_db != nullptr) ok = __ldg(group_db + row) != grp;
+                    // k = 1 keeps its best row in a register, so it has to check the group right here
+                    if (E == 0 && ok && grp >= 0 && group_db != nullptr) ok = __ldg(group_db + row) != grp;
                     if (ok) {
                         if constexpr (E > 0) {
                             st.buf[st.cnt++] = make_key(s, row);
@@ -264,11 +290,13 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
 // A buffer whose candidates all sit in its first 32*ES slots: sort only those (warp-cooperative) and write the k
 // output entries.  Returns the k-th best key (0 when fewer than k candidates exist).
 template <int ES>
-__device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* out, int k) {
+__device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* out, int k, int grp,
+                                                 const int32_t* __restrict__ group_db) {
     const int lane = threadIdx.x & 31;
     uint64_t key[ES];
 #pragma unroll
     for (int e = 0; e < ES; ++e) key[e] = __ldcg(reinterpret_cast<const unsigned long long*>(b + e * 32 + lane));
+    drop_same_group<ES>(key, grp, group_db);
     warp_bitonic_sort_desc<ES>(key);
 #pragma unroll
     for (int e = 0; e < ES; ++e) {
@@ -291,22 +319,23 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
             if (qr >= p.nq) break;
             uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
             uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
+            const int grp_l = __shfl_sync(0xffffffffu, st.grp, l);
             uint64_t kth;
             if constexpr (E <= 16) {
                 // Later slices start from a good shared threshold and often collect only a handful of rows: sort
                 // just the filled prefix then (32 slots cost a fifth of the 128-slot network of k = 50).
                 const int cnt_l = (p.dbg & 32) ? 32 * E : __shfl_sync(0xffffffffu, st.cnt, l);
                 if (E > 1 && cnt_l <= 32) {
-                    kth = flush_prefix<1>(b, out, p.k);
+                    kth = flush_prefix<1>(b, out, p.k, grp_l, p.group_db);
                 } else if (E > 2 && cnt_l <= 64) {
-                    kth = flush_prefix<2>(b, out, p.k);
+                    kth = flush_prefix<2>(b, out, p.k, grp_l, p.group_db);
                 } else if (E > 4 && cnt_l <= 128) {
-                    kth = flush_prefix<4>(b, out, p.k);
+                    kth = flush_prefix<4>(b, out, p.k, grp_l, p.group_db);
                 } else if (E > 8 && cnt_l <= 256) {
-                    kth = flush_prefix<8>(b, out, p.k);
+                    kth = flush_prefix<8>(b, out, p.k, grp_l, p.group_db);
                 } else {
                     uint64_t key[E];
-                    kth = warp_compact<E>(b, p.k, key);
+                    kth = warp_compact<E>(b, p.k, key, grp_l, p.group_db);
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         const int pos = e * 32 + lane;
@@ -314,7 +343,7 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
                     }
                 }
             } else {
-                kth = warp_compact_mem<E>(b, p.k);
+                kth = warp_compact_mem<E>(b, p.k, grp_l, p.group_db);
                 for (int pos = lane; pos < p.k; pos += 32)
                     out[pos] = __ldcg(reinterpret_cast<const unsigned long long*>(b + pos));
             }
@@ -474,6 +503,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
             item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C);
+            if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -1008,6 +1038,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
             item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
+            if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -1202,6 +1233,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
             item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
+            if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();

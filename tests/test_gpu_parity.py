@@ -295,6 +295,33 @@ def test_self_and_group_exclusion(metric, k):
         assert self_ids[i] not in I[i]
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("k", [1, 5, 20, 100, 300])
+def test_group_exclusion_with_large_groups_of_near_duplicates(k, variant):
+    """Every query has 40 near-duplicates in its own group: they outscore everything else, fill the candidate
+    buffers (the group check runs when a buffer is sorted, not per row) and must all be gone from the result.
+    Several database slices, every buffer size (k = 5 / 20 / 100 / 300), all kernel variants."""
+    rng = np.random.default_rng(100 + k)
+    d, n_groups, per = 64, 60, 40
+    base = unit_rows(rng, n_groups, d)
+    dup = base[:, None, :] + 0.02 * rng.standard_normal((n_groups, per, d), dtype=np.float32)
+    filler = unit_rows(rng, 9000, d)
+    xb = np.concatenate([dup.reshape(-1, d), filler]).astype(np.float32)
+    gdb = np.concatenate([np.repeat(np.arange(n_groups), per), n_groups + np.arange(9000) // 3]).astype(np.int32)
+    perm = rng.permutation(len(xb))
+    xb, gdb = O.bf16_round(xb[perm]), gdb[perm]
+    self_ids = np.flatnonzero(gdb < n_groups)[::7].astype(np.int32)        # queries = some of the duplicates
+    xq, gq = xb[self_ids].copy(), gdb[self_ids].copy()
+    D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_IP, self_ids=self_ids, group_db=gdb, group_q=gq)
+    idx = make_index(d, "ip", "bf16")
+    idx.add(xb)
+    idx.set_groups(gdb)
+    D, I = idx.search(xq, k, self_ids=self_ids, group_q=gq, force_variant=variant, force_slices=3)
+    idx.close()
+    assert_parity(D, I, D_ref, I_ref, "ip", tie_tol=2e-5)
+    assert not np.any(gdb[I] == gq[:, None])
+
+
 def test_mine_hard_negatives_self_join():
     from cloudvectordb_b200 import mine_hard_negatives
     rng = np.random.default_rng(22)
