@@ -346,8 +346,10 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     //   4 = CTA pair with all of K <= 768 in TMEM and 64-column accumulators (comparison only).
     const bool ts2_ok = ix->planes == 1 && p.nkb <= 13;  // padded K <= 832 (768 + the L2 norm columns)
     int variant = 1;
-    if (ts2_ok && nq > 256) {
-        // large batches: resident queries win for K >= 448 and for k = 1; for short K with a real top-k the
+    if (ts2_ok && nq > 128) {
+        // more than one 128-query tile: the CTA-pair kernels take 256 queries per pass over the database (129..256
+        // queries on 12.5M x 768: 4.1-4.8 ms against 5.5-6.6 ms for two passes of the single-CTA kernel --
+        // tools/ridge_probe.py).  Resident queries win for K >= 448 and for k = 1; for short K with a real top-k the
         // 256 x 256 streaming pair kernel is ahead (K = 384, k = 10: 1325 vs 1236 TFLOP/s), and for K <= 128 the
         // single-CTA kernel (841 vs 804 / 707) -- tools/variant_sweep.py
         if (p.nkb <= 2) variant = 1;
