@@ -470,7 +470,16 @@ constexpr int kGroupedBlockN = 128;
 // (device pointers; D/I device outputs).
 int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, const int32_t* probes, int nprobe,
                         float* D, int64_t* I, cudaStream_t st) {
-    const int E = pick_E(k);
+    // Every (query, list) pair starts its scan cold and a list is only a few hundred rows, so about
+    // k * (1 + ln(rows / k)) rows pass the filter per pair.  Larger buffers (fewer sorts) were measured and do not
+    // help (4M x 768, nlist 8192, nprobe 8, 10k queries: 3.58 / 3.60 / 3.95 ms per batch with 1x / 2x / 4x the flat
+    // buffer size): the cost is the candidate walk itself, serialised in the one warp that owns the few valid
+    // query rows of an item.  CVDB_IVF_EMULT = 2, 4 re-runs that experiment.
+    int E = pick_E(k);
+    if (const char* env = getenv("CVDB_IVF_EMULT")) {
+        const int mult = std::max(1, atoi(env));
+        if (E >= 1 && E < 16) E = std::min(16, E * mult);
+    }
     const int C = 32 * (E ? E : 1);
     const int l2 = ix->metric == CVDB_METRIC_L2;
     const int64_t n_pairs = nq * nprobe;

@@ -564,24 +564,44 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
     }
     const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
     if (!__any_sync(0xffffffffu, m > st.thr)) return;
+    if constexpr (E >= 2) {
+        // as in scan_chunk: room for a whole chunk once, then only the lanes with a candidate walk their groups
+        make_room<E, false>(st, k, room);
+        if (m > st.thr) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
-        // rows of a list are stored in no particular id order: equal scores must stay candidates (keys decide)
-        if constexpr (E > 0) make_room<E, false>(st, k, room);
+            for (int g = 0; g < 4; ++g) {
+                if (!(m8[g] > st.thr)) continue;
 #pragma unroll
-        for (int j = 8 * g; j < 8 * g + 8; ++j) {
-            const float s = __uint_as_float(v[j]);
-            const uint32_t row = row0 + j;
-            if (s > st.thr && row < row_end) {
-                const uint32_t id = row_ids ? static_cast<uint32_t>(__ldg(row_ids + row)) : row;
-                if constexpr (E > 0) {
-                    st.buf[st.cnt++] = make_key(s, id);
-                } else {
-                    // top-1: ids are not visited in increasing order here, so ties go through the key
-                    const uint64_t key = make_key(s, id);
-                    if (key > st.best) st.best = key;
-                    st.thr = thr_from_shared(static_cast<uint32_t>(st.best >> 32));  // equal scores still pass
+                for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                    const float s = __uint_as_float(v[j]);
+                    const uint32_t row = row0 + j;
+                    if (s > st.thr && row < row_end) {
+                        const uint32_t id = row_ids ? static_cast<uint32_t>(__ldg(row_ids + row)) : row;
+                        st.buf[st.cnt++] = make_key(s, id);
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (!__any_sync(0xffffffffu, m8[g] > st.thr)) continue;
+            // rows of a list are stored in no particular id order: equal scores must stay candidates (keys decide)
+            if constexpr (E > 0) make_room<E, false>(st, k, room);
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                const float s = __uint_as_float(v[j]);
+                const uint32_t row = row0 + j;
+                if (s > st.thr && row < row_end) {
+                    const uint32_t id = row_ids ? static_cast<uint32_t>(__ldg(row_ids + row)) : row;
+                    if constexpr (E > 0) {
+                        st.buf[st.cnt++] = make_key(s, id);
+                    } else {
+                        // top-1: ids are not visited in increasing order here, so ties go through the key
+                        const uint64_t key = make_key(s, id);
+                        if (key > st.best) st.best = key;
+                        st.thr = thr_from_shared(static_cast<uint32_t>(st.best >> 32));  // equal scores still pass
+                    }
                 }
             }
         }
@@ -750,12 +770,24 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     uint64_t* out = p.part + static_cast<size_t>(dst_l) * p.k;
                     uint64_t kth;
                     if constexpr (E <= 16) {
-                        uint64_t key[E];
-                        kth = warp_compact<E>(b, p.k, key);
+                        // a list is a few hundred rows: most buffers hold a few dozen candidates
+                        const int cnt_l = __shfl_sync(0xffffffffu, st.cnt, l);
+                        if (E > 1 && cnt_l <= 32) {
+                            kth = flush_prefix<1>(b, out, p.k, -1, nullptr);
+                        } else if (E > 2 && cnt_l <= 64) {
+                            kth = flush_prefix<2>(b, out, p.k, -1, nullptr);
+                        } else if (E > 4 && cnt_l <= 128) {
+                            kth = flush_prefix<4>(b, out, p.k, -1, nullptr);
+                        } else if (E > 8 && cnt_l <= 256) {
+                            kth = flush_prefix<8>(b, out, p.k, -1, nullptr);
+                        } else {
+                            uint64_t key[E];
+                            kth = warp_compact<E>(b, p.k, key);
 #pragma unroll
-                        for (int e = 0; e < E; ++e) {
-                            const int pos = e * 32 + lane;
-                            if (pos < p.k) out[pos] = key[e];
+                            for (int e = 0; e < E; ++e) {
+                                const int pos = e * 32 + lane;
+                                if (pos < p.k) out[pos] = key[e];
+                            }
                         }
                     } else {
                         kth = warp_compact_mem<E>(b, p.k);
