@@ -542,7 +542,7 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
         p.part = ix->part.as<uint64_t>();
         p.gthr = ix->gthr.as<uint32_t>();
         CUtensorMap tq, tx;
-        TRY(make_tmap_2d(&tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 128));
+        TRY(make_tmap_2d(&tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 32));  // four 32-row boxes per A tile
         TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, kGroupedBlockN));
         LAUNCH(launch_grouped(E, tq, tx, p, grid, st));
     }

@@ -666,12 +666,20 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const GroupItem it = p.items[w];
             const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
+            // An item usually has far fewer than 128 query rows.  Packed into consecutive tile rows they would all
+            // sit in TMEM lanes 0.. and be scanned by a single epilogue warp, so the A tile is loaded as four
+            // 32-row boxes, box j starting at the item's j-th quarter: every epilogue warp gets a quarter of the
+            // pairs (the other rows of a box are somebody else's pairs; their lanes stay idle).
+            const int q4 = (it.a_rows + 3) >> 2;
             for (int t = 0; t < n_tiles; ++t) {
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (elect_one_sync()) {
                         mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                        tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES, kb * BLOCK_K, it.a_row0, kEvictNormal);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES + j * (A_BYTES / 4), kb * BLOCK_K,
+                                        it.a_row0 + j * q4, kEvictNormal);
                         tma_load_2d(&tmap_x, &full_bar[stage], smem_b + stage * B_BYTES, kb * BLOCK_K,
                                     it.x_row0 + t * BLOCK_N, kEvictNormal);
                     }
@@ -725,8 +733,9 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const GroupItem it = p.items[w];
             const int n_tiles = (it.x_rows + BLOCK_N - 1) / BLOCK_N;
-            const int a_local = ewarp * 32 + static_cast<int>(lane);
-            const bool valid = a_local < it.a_rows;
+            const int q4 = (it.a_rows + 3) >> 2;  // query rows per epilogue warp (see the producer)
+            const int a_local = ewarp * q4 + static_cast<int>(lane);
+            const bool valid = static_cast<int>(lane) < q4 && a_local < it.a_rows;
             const int a_row = it.a_row0 + a_local;
             const int query = valid ? __ldg(p.pair_query + a_row) : 0;
             const int dst = valid ? __ldg(p.pair_dst + a_row) : -1;
