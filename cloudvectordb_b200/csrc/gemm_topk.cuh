@@ -553,7 +553,9 @@ constexpr size_t gemm_topk_ss_smem_bytes() {
 // ===========================================================================
 template <int E>
 __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0,
-                                                   uint32_t row_end, const int32_t* __restrict__ row_ids, int k, int room) {
+                                                   uint32_t row_end, uint32_t lane_id, int k, int room) {
+    // lane_id: the caller's row id of the chunk's column `lane` (the ids of a chunk are the same for every query
+    // row, so the warp loads them once, ahead of time, instead of one dependent lookup per candidate)
     float m8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -564,6 +566,9 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
     }
     const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
     if (!__any_sync(0xffffffffu, m > st.thr)) return;
+    uint32_t id[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) id[j] = __shfl_sync(0xffffffffu, lane_id, j);
     if constexpr (E >= 2) {
         // as in scan_chunk: room for a whole chunk once, then only the lanes with a candidate walk their groups
         make_room<E, false>(st, k, room);
@@ -575,10 +580,7 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
                 for (int j = 8 * g; j < 8 * g + 8; ++j) {
                     const float s = __uint_as_float(v[j]);
                     const uint32_t row = row0 + j;
-                    if (s > st.thr && row < row_end) {
-                        const uint32_t id = row_ids ? static_cast<uint32_t>(__ldg(row_ids + row)) : row;
-                        st.buf[st.cnt++] = make_key(s, id);
-                    }
+                    if (s > st.thr && row < row_end) st.buf[st.cnt++] = make_key(s, id[j]);
                 }
             }
         }
@@ -593,12 +595,11 @@ __device__ __forceinline__ void scan_chunk_grouped(LaneTopk<E>& st, const uint32
                 const float s = __uint_as_float(v[j]);
                 const uint32_t row = row0 + j;
                 if (s > st.thr && row < row_end) {
-                    const uint32_t id = row_ids ? static_cast<uint32_t>(__ldg(row_ids + row)) : row;
                     if constexpr (E > 0) {
-                        st.buf[st.cnt++] = make_key(s, id);
+                        st.buf[st.cnt++] = make_key(s, id[j]);
                     } else {
                         // top-1: ids are not visited in increasing order here, so ties go through the key
-                        const uint64_t key = make_key(s, id);
+                        const uint64_t key = make_key(s, id[j]);
                         if (key > st.best) st.best = key;
                         st.thr = thr_from_shared(static_cast<uint32_t>(st.best >> 32));  // equal scores still pass
                     }
@@ -751,9 +752,16 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
             const uint32_t row_end = static_cast<uint32_t>(it.x_row0 + it.x_rows);
             for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t row0 = static_cast<uint32_t>(it.x_row0 + t * BLOCK_N);
+                // row ids of the tile's columns, one chunk of 32 per register, fetched while the MMA still runs
+                uint32_t tile_id[BLOCK_N / 32];
+#pragma unroll
+                for (int q = 0; q < BLOCK_N / 32; ++q) {
+                    const uint32_t r = row0 + q * 32 + lane;
+                    tile_id[q] = (p.row_ids != nullptr && r < row_end) ? static_cast<uint32_t>(__ldg(p.row_ids + r)) : r;
+                }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t row0 = static_cast<uint32_t>(it.x_row0 + t * BLOCK_N);
                 const uint32_t taddr = tmem_base + lane_base + acc * BLOCK_N;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 32) {
@@ -764,7 +772,11 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                         tc_fence_before();
                         mbar_arrive(&tmem_empty[acc]);
                     }
-                    scan_chunk_grouped<E>(st, v, row0 + c, row_end, p.row_ids, p.k, p.room);
+                    uint32_t lane_id = tile_id[0];
+#pragma unroll
+                    for (int q = 1; q < BLOCK_N / 32; ++q)
+                        if (c == q * 32) lane_id = tile_id[q];
+                    scan_chunk_grouped<E>(st, v, row0 + c, row_end, lane_id, p.k, p.room);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
