@@ -405,8 +405,11 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->waves.as<uint32_t>();
     }
 
+    // a single partial query tile on the single-CTA kernel (small, HBM-bound batches): give every epilogue warp a
+    // quarter of the queries instead of filling the TMEM lanes from 0 up, where 32 queries are one warp's work
+    p.a_quarter = (variant == 1 && nq < 128 && !(opts && (opts->debug_flags & 64))) ? static_cast<int>(ceil_div(nq, 4)) : 0;
     CUtensorMap tq, tx;
-    TRY(make_tmap_2d(&tq, ix->q_pack.p, nq_pad, ix->row_elems, 128));
+    TRY(make_tmap_2d(&tq, ix->q_pack.p, nq_pad, ix->row_elems, p.a_quarter > 0 ? 32 : 128));
     TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;

@@ -277,7 +277,8 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
     constexpr int C = 32 * (E > 0 ? E : 1);
     const uint32_t lane = threadIdx.x & 31;
     st.gq = (q_valid && p.gthr != nullptr) ? p.gthr + q_row : nullptr;
-    st.thr = st.gq ? thr_from_shared(__ldcg(st.gq)) : -INFINITY;
+    // padding lanes (and, in a quartered small-batch tile, lanes that see another warp's query) never collect
+    st.thr = !q_valid ? INFINITY : (st.gq ? thr_from_shared(__ldcg(st.gq)) : -INFINITY);
     if constexpr (E > 0) {
         st.cnt = 0;
         for (int i = lane; i < 32 * C; i += 32) warp_buf[i] = 0;  // the warp's 32 buffers are contiguous
@@ -310,11 +311,11 @@ __device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* ou
 // End of a work item: sorted top-k of every query of the warp -> part[q][slice][0..k).
 template <int E>
 __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams& p, int q_base, int q_row, bool q_valid,
-                                           int slice) {
+                                           int slice, int q_lanes = 32) {
     const uint32_t lane = threadIdx.x & 31;
     if constexpr (E > 0) {
         __syncwarp();
-        for (int l = 0; l < 32; ++l) {
+        for (int l = 0; l < q_lanes; ++l) {
             const int qr = q_base + l;
             if (qr >= p.nq) break;
             uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
@@ -430,8 +431,17 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (elect_one_sync()) {
                             mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                            tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES, a_col + kb * BLOCK_K,
-                                        qt * BLOCK_M, kEvictLast);
+                            if (p.a_quarter > 0) {
+                                // a small batch: spread its queries over the four epilogue warps (tmap_q has 32-row
+                                // boxes then; the rows a box holds beyond its quarter stay idle lanes)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES + j * (A_BYTES / 4),
+                                                a_col + kb * BLOCK_K, j * p.a_quarter, kEvictLast);
+                            } else {
+                                tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * A_BYTES, a_col + kb * BLOCK_K,
+                                            qt * BLOCK_M, kEvictLast);
+                            }
                             tma_load_2d(&tmap_x, &full_bar[stage], smem_b + stage * B_BYTES, b_col + kb * BLOCK_K,
                                         t * BLOCK_N, kEvictNormal);
                         }
@@ -498,8 +508,10 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
             const int t0 = slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-            const int q_row = qt * BLOCK_M + ewarp * 32 + lane;
-            const bool q_valid = q_row < p.nq;
+            const int q_lanes = p.a_quarter > 0 ? p.a_quarter : 32;  // query rows owned by this warp
+            const int q_base = qt * BLOCK_M + ewarp * q_lanes;
+            const int q_row = q_base + static_cast<int>(lane);
+            const bool q_valid = static_cast<int>(lane) < q_lanes && q_row < p.nq;
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
             item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C);
@@ -527,7 +539,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            item_flush<E>(st, p, qt * BLOCK_M + ewarp * 32, q_row, q_valid, slice);
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice, q_lanes);
         }
     }
 

@@ -29,6 +29,8 @@ struct GemmTopkParams {
     uint32_t* gthr;  // [nq] shared per-query threshold (ordered-float), zeroed before the launch
     uint32_t* wave_cnt;  // [waves] producers that finished issuing the loads of their item in that wave (or null)
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
+    int a_quarter;   // single-CTA kernel with one partial query tile: query rows per epilogue warp (the A tile is
+                     // loaded as four 32-row boxes, box j = queries [j*a_quarter, j*a_quarter + 32)); 0 = one box
 };
 
 struct GroupItem {

@@ -70,8 +70,9 @@ typedef struct cvdb_search_opts {
     int debug_flags;         /* kernel-tuning experiments only (results become invalid): 1 = skip the
                                 top-k scan, 2 = skip the TMEM read as well, 4 = no threshold sharing between slices,
                                 8 = no wave alignment of the producers, 16 = run all K-steps of the padded row width,
-                                32 = always sort the whole candidate buffer at the end of a work item
-                                (4, 8, 16 and 32 leave the results valid) */
+                                32 = always sort the whole candidate buffer at the end of a work item,
+                                64 = small batches: fill the query tile from row 0 up instead of one quarter per
+                                epilogue warp (4, 8, 16, 32 and 64 leave the results valid) */
 } cvdb_search_opts;
 
 /* -- index lifetime -------------------------------------------------------
