@@ -274,10 +274,11 @@ def test_bf16_recall_against_fp32_oracle():
 
 
 # ---- exclusion (hard-negative mining) -----------------------------------------------------
+@pytest.mark.parametrize("nq", [150, 37, 5])          # two query tiles / one partial tile split over the four epilogue warps
 @pytest.mark.parametrize("metric,k", [("ip", 10), ("l2", 50)])
-def test_self_and_group_exclusion(metric, k):
+def test_self_and_group_exclusion(metric, k, nq):
     rng = np.random.default_rng(21)
-    n, d, nq = 6000, 96, 150
+    n, d = 6000, 96
     xb = O.bf16_round(unit_rows(rng, n, d))
     self_ids = rng.integers(0, n, nq).astype(np.int32)
     xq = xb[self_ids].copy()
