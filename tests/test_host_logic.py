@@ -200,3 +200,53 @@ def test_sharded_search_world2_gloo(metric):
     for rank, D, I, D2, I2 in outs:
         assert np.array_equal(I, I_ref) and np.allclose(D, D_ref, atol=1e-5)
         assert np.array_equal(I2, I2_ref) and np.allclose(D2, D2_ref, atol=1e-5)
+
+
+def _mining_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cloudvectordb_b200.mining import mine_hard_negatives_sharded
+        rng = np.random.default_rng(11)
+        n, d, k = 501, 10, 7
+        emb = rng.standard_normal((n, d), dtype=np.float32)
+        groups = (np.arange(n) // 3).astype(np.int32)
+        lo, hi = (0, 300) if rank == 0 else (300, n)               # uneven shards, ragged last chunk
+        idx = ShardedIndex(d, "ip", local_index=OracleLocalIndex(d, "ip"), merge_fn=oracle_merge)
+        idx.add_local(emb[lo:hi])
+        assert idx.ntotal == n and idx.id_base == lo
+        idx.set_groups_local(groups[lo:hi])
+        D, I = mine_hard_negatives_sharded(idx, torch.from_numpy(emb[lo:hi]), k, torch.from_numpy(groups[lo:hi]), chunk=128)
+        q.put((rank, lo, hi, D.numpy(), I.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_mining_world2_gloo():
+    """configs[2] host logic on CPU: anchor chunks broadcast from their owner, global self ids mapped to the
+    shard that holds them, groups broadcast with the chunk, per-rank candidates all-gathered and merged."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mining_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(11)
+    n, d, k = 501, 10, 7
+    emb = rng.standard_normal((n, d), dtype=np.float32)
+    groups = (np.arange(n) // 3).astype(np.int32)
+    D_ref, I_ref = O.search_ref(emb, emb, k, O.METRIC_IP, self_ids=np.arange(n), group_db=groups, group_q=groups)
+    seen = 0
+    for rank, lo, hi, D, I in outs:
+        assert D.shape == (hi - lo, k)
+        assert np.array_equal(I, I_ref[lo:hi]) and np.allclose(D, D_ref[lo:hi], atol=1e-5)
+        assert not np.any(I == np.arange(lo, hi)[:, None])
+        assert not np.any(groups[I] == groups[lo:hi, None])
+        seen += hi - lo
+    assert seen == n
