@@ -90,6 +90,21 @@ def cpu_sample_qps(a, steps, warmup):
     xb = O.bf16_round(O.synth_rows(DB_SEED, 0, rows, a.dim))
     xq = O.bf16_round(O.synth_rows(Q_SEED, 0, nq, a.dim))
     metric = O.METRIC_IP if a.metric == "ip" else O.METRIC_L2
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: give the BLAS every core this process may run on, and
+    # report the thread count it really uses
+    limiter = None
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        limiter = threadpool_limits(limits=cores, user_api="blas")
+        used = [i["num_threads"] for i in threadpool_info() if i.get("user_api") == "blas"]
+        if used:
+            cores = max(used)
+    except Exception:
+        pass
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -97,12 +112,10 @@ def cpu_sample_qps(a, steps, warmup):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+    if limiter is not None:
+        limiter.restore_original_limits()
     t = float(np.mean(times))
     qps_full = nq / t * (rows / a.rows)
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count()
     return {"value": qps_full, "unit": "queries/s", "cores": cores, "kind": "port",
             "sample": f"{nq} queries x {rows} rows x {a.dim} (NumPy/OpenBLAS fp32 oracle, {t*1e3:.0f} ms per pass), "
                       f"scaled by rows to the {a.rows}-row database"}, t
