@@ -1,24 +1,32 @@
 """Headline benchmark: queries/sec of exact top-10 inner-product search,
-10M x 768 bf16 database, 10k-query batches (BASELINE.json configs[1]).
+10M x 768 bf16 database, 10k-query batches (BASELINE.json configs[1]) -- plus one bounded,
+driver-visible measurement of every other BASELINE.json config in the same JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs all|none|0,2,3,4,ingest]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one search of the whole query batch against the whole database.
 With N > 1 the database is row-sharded over the ranks (strong scaling: total
-work fixed), every rank searches its shard, one NCCL all-gather exchanges the
-per-rank candidates and each rank does the final k-way select.
+work fixed), every rank searches its shard, ONE NCCL all-gather exchanges the
+per-rank candidates (64-bit keys) and each rank does the final k-way merge.
 
 Prints ONE JSON line (rank 0).  `value` is timed with the queries already in
 HBM; `e2e` goes through the public API with pinned HOST buffers (host->device
 copy of the queries and device->host copy of (D, I) inside the timed region).
+`configs` holds one record per other BASELINE.json config, each with its own
+`roofline` block:
+    configs[0]  exact top-10 IP, 100k x 384 fp32, 10k queries                    (replica per rank)
+    configs[2]  one 65 536-anchor hard-negative mining chunk, k=50, self + group exclusion, against the
+                headline database (rows split over the N ranks)
+    configs[3]  one Lloyd iteration, 100M x 384 points split over the N ranks, 65 536 centroids
+    configs[4]  small-batch latency, nq in {1, 16, 64}, 12.5M x 768 rows PER rank, >= 200 distinct batches
+    ingest      host -> HBM add() rate, fp32 rows, pageable and pinned source (N = 1 only)
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -29,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CHUNK = 65536          # rows per seeded generator chunk (same data for every N)
-DB_SEED, Q_SEED = 1234, 5678
+DB_SEED, Q_SEED, KM_SEED, LAT_SEED = 1234, 5678, 4242, 777_000
 
 
 def parse():
@@ -48,6 +56,10 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="database rows of the bounded CPU sample")
     ap.add_argument("--cpu-nq", type=int, default=2048, help="queries of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check-queries", type=int, default=1024, help="queries of the batch checked against torch fp32")
+    ap.add_argument("--configs", default="all", help="all | none | comma list of 0,2,3,4,ingest")
+    ap.add_argument("--km-points", type=int, default=100_000_000, help="configs[3]: points in total (split over the ranks)")
+    ap.add_argument("--lat-rows", type=int, default=12_500_000, help="configs[4]: database rows PER rank")
     ap.add_argument("--dbg", type=int, default=0, help="kernel debug flags (tuning experiments)")
     ap.add_argument("--slices", type=int, default=0, help="override the database-slice heuristic")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 streaming kernel, 2 CTA-pair/TMEM kernel")
@@ -67,7 +79,7 @@ def workload_config(a, world):
             "k": a.k, "metric": a.metric,
             "distribution": ("iid unit-norm Gaussian rows" if a.dist == "iid" else
                              "clustered: 4096 centres + 0.3 noise, queries = rows + 0.1 noise") + ", seeds 1234/5678",
-            "sharding": f"rows split over {world} rank(s), one all-gather of (D,I) + k-way select",
+            "sharding": f"rows split over {world} rank(s), one all-gather of [nq,k] 64-bit candidate keys + k-way merge",
             "cache": "inputs larger than L2 (database 15.4 GB vs 126 MB L2), no explicit flush"}
 
 
@@ -81,9 +93,20 @@ def load_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def measured_traffic(n_gpus):
+    """DRAM bytes per launch of the dominant kernel from an ncu capture OF THIS N (profiles/roofline_traffic.json,
+    keyed by the number of GPUs); None when no capture exists for it -- never a number measured at another N."""
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        j = json.load(open(tp))
+        return j.get("by_n_gpus", {}).get(str(n_gpus), {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------- CPU arm
 def cpu_sample_qps(a, steps, warmup):
-    """The oracle (NumPy fp32 sgemm + select, all host threads) on a bounded sample of the
+    """The oracle (NumPy fp32 sgemm + vectorised select, all host threads) on a bounded sample of the
     workload; scaled to full-size queries/sec by rows_sample / rows (cost is linear in rows)."""
     from oracle import flat_oracle as O
     rows, nq = min(a.cpu_rows, a.rows), min(a.cpu_nq, a.nq)
@@ -112,11 +135,18 @@ def cpu_sample_qps(a, steps, warmup):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+    # the sgemm alone, to show how much of a pass is BLAS and how much is selection
+    t0 = time.perf_counter()
+    _ = xq @ xb[:min(rows, 262144)].T
+    t_gemm = (time.perf_counter() - t0) * rows / min(rows, 262144)
     if limiter is not None:
         limiter.restore_original_limits()
     t = float(np.mean(times))
     qps_full = nq / t * (rows / a.rows)
+    flops = 2.0 * nq * rows * a.dim
     return {"value": qps_full, "unit": "queries/s", "cores": cores, "kind": "port",
+            "gflops_whole_pass": flops / t / 1e9, "gflops_sgemm_alone": flops / t_gemm / 1e9,
+            "sgemm_share_of_pass": min(1.0, t_gemm / t),
             "sample": f"{nq} queries x {rows} rows x {a.dim} (NumPy/OpenBLAS fp32 oracle, {t*1e3:.0f} ms per pass), "
                       f"scaled by rows to the {a.rows}-row database"}, t
 
@@ -190,11 +220,13 @@ class ClockSampler:
                 "source": "NVML, 200 ms period, during the timed region"}
 
 
-# --------------------------------------------------------------------------- GPU arm
+# --------------------------------------------------------------------------- synthetic data
 def gen_rows(torch, dev, seed, lo, hi, d, dtype, centres=None, noise=0.3):
     """Rows [lo, hi) of the synthetic unit-norm matrix; chunk c uses generator seed+c.
     With `centres` the rows are centre[random] + noise * N(0, I) (the clustered distribution of SURVEY.md 8(d))."""
     out = torch.empty((hi - lo, d), dtype=dtype, device=dev)
+    if hi <= lo:
+        return out
     c0, c1 = lo // CHUNK, (hi - 1) // CHUNK
     for c in range(c0, c1 + 1):
         g = torch.Generator(device=dev).manual_seed(seed + c)
@@ -208,11 +240,57 @@ def gen_rows(torch, dev, seed, lo, hi, d, dtype, centres=None, noise=0.3):
     return out
 
 
+def count_beyond_tie(D, I, D_ref, I_ref, tol):
+    """Entries whose id differs from the reference although the two scores at that rank differ by more than
+    `tol` (north_star: "indices identical except for ties within ...")."""
+    D, D_ref = np.asarray(D, np.float64), np.asarray(D_ref, np.float64)
+    return int(((np.asarray(I) != np.asarray(I_ref)) & ~(np.abs(D - D_ref) <= tol)).sum())
+
+
+class TorchRef:
+    """fp32 torch.matmul top-k over row chunks, merged over the ranks: the in-bench check of a query subsample
+    (a torch fp32 reference, not the oracle: bench.py may use oracle/ only for the CPU baseline)."""
+
+    def __init__(self, torch, dist, world, dev, k, metric):
+        self.torch, self.dist, self.world, self.dev, self.k, self.metric = torch, dist, world, dev, k, metric
+
+    def topk(self, qs, blocks, self_ids=None, group_q=None, group_of=None):
+        """blocks: iterable of (global row offset, fp32 rows [m, d]).  Returns (D, I) numpy, merged over ranks."""
+        torch, k = self.torch, self.k
+        nchk = qs.shape[0]
+        best_v = torch.full((nchk, k), -float("inf"), device=self.dev)
+        best_i = torch.full((nchk, k), -1, dtype=torch.int64, device=self.dev)
+        for r0, blk in blocks:
+            s = qs @ blk.T
+            if self.metric == "l2":
+                s = -((qs * qs).sum(1)[:, None] - 2 * s + (blk * blk).sum(1)[None, :])
+            ids = torch.arange(r0, r0 + blk.shape[0], device=self.dev)
+            if self_ids is not None:
+                s = s.masked_fill(ids[None, :] == self_ids[:, None], -float("inf"))
+            if group_q is not None:
+                s = s.masked_fill(group_of(ids)[None, :] == group_q[:, None], -float("inf"))
+            v, i = torch.topk(s, min(k, blk.shape[0]), dim=1)
+            cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i + r0], 1)
+            o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :k]
+            best_v, best_i = torch.gather(cv, 1, o), torch.gather(ci, 1, o)
+        if self.world > 1:
+            gv = [torch.empty_like(best_v) for _ in range(self.world)]
+            gi = [torch.empty_like(best_i) for _ in range(self.world)]
+            self.dist.all_gather(gv, best_v)
+            self.dist.all_gather(gi, best_i)
+            cv, ci = torch.cat(gv, 1), torch.cat(gi, 1)
+            o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :k]
+            best_v, best_i = torch.gather(cv, 1, o), torch.gather(ci, 1, o)
+        D = best_v if self.metric == "ip" else -best_v
+        return D.cpu().numpy(), best_i.cpu().numpy()
+
+
+# --------------------------------------------------------------------------- GPU arm
 def run_ours(a):
     import torch
     import torch.distributed as dist
 
-    from cloudvectordb_b200 import IndexFlat, ShardedIndex, _C
+    from cloudvectordb_b200 import IndexFlat, Kmeans, ShardedIndex, _C
     from cloudvectordb_b200.sharded import shard_bounds
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +303,8 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     lib = _C.lib()
     peaks = load_peaks()
+    peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    which = {"all": {"0", "2", "3", "4", "ingest"}, "none": set()}.get(a.configs, set(a.configs.split(",")))
 
     lo, hi = shard_bounds(a.rows, world, rank)
     centres = None
@@ -249,12 +329,12 @@ def run_ours(a):
         xq = gen_rows(torch, dev, Q_SEED, 0, a.nq, a.dim, torch.bfloat16)
     if world > 1:
         index = ShardedIndex(a.dim, a.metric, "bf16", device=local_rank)
-        index.local.reserve(hi - lo)
+        index.local.reserve(max(hi - lo, a.lat_rows if "4" in which else 0))
         index.add_local(xb)
         local = index.local
     else:
         index = IndexFlat(a.dim, a.metric, "bf16", device=local_rank)
-        index.reserve(hi - lo)
+        index.reserve(max(hi - lo, a.lat_rows if "4" in which else 0))
         index.add(xb)
         local = index
     q_host = xq.cpu().pin_memory()
@@ -271,13 +351,20 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def step_device():
         return index.search(xq, a.k, profile=True, **vkw)
 
     def step_e2e():
         return index.search(q_host, a.k, **vkw)
 
-    def timed(fn, steps, warmup, collect_kernel=False):
+    def timed(fn, steps, warmup, collect_kernel=False, prof_index=None):
+        prof_index = prof_index or local
         for _ in range(warmup):
             fn()
         barrier()
@@ -285,18 +372,16 @@ def run_ours(a):
         kms = []
         e0.record()
         if collect_kernel:
-            local.profile_ms()  # drop warm-up launches
+            prof_index.profile_ms()  # drop warm-up launches
         for _ in range(steps):
             out = fn()
         e1.record()
         torch.cuda.synchronize()
         if collect_kernel:
-            kms = local.profile_ms()[-steps:]
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            kms = prof_index.profile_ms()
+        ms = e0.elapsed_time(e1)
         barrier()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), kms, out
+        return max_over_ranks(ms), kms, out
 
     sampler = ClockSampler(local_rank)
     launches0 = lib.cvdb_kernel_launches()
@@ -307,6 +392,7 @@ def run_ours(a):
     launches = (lib.cvdb_kernel_launches() - launches0) * a.steps // (a.steps + a.warmup)
     ms_per_step = total_ms / a.steps
     value = a.nq / ms_per_step * 1e3
+    kms = kms[-a.steps:]
 
     # end to end through the public API with pinned host buffers
     e2e_ms, _, (Dh, Ih) = timed(step_e2e, max(2, a.steps // 2), 2)
@@ -318,72 +404,261 @@ def run_ours(a):
     w = local.last_work()
     kernel_ms = float(np.mean(kms))
     achieved = w["flops"] / kernel_ms / 1e9
-    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "tensor", "kernel": "gemm_topk", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "peak_kind": "sustained cuBLAS bf16, " + peaks["source"],
+    roofline = {"bound": "tensor", "kernel": "gemm_topk", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "peak_kind": "sustained cuBLAS bf16, " + peaks["source"],
                 "peak_burst": peaks["bf16_tflops"], "frac_burst": achieved / peaks["bf16_tflops"],
                 "frac_nominal_2250": achieved / 2250.0, "kernel_ms": kernel_ms,
                 "kernel_share_of_step": kernel_ms / ms_per_step, "flops_per_launch": w["flops"],
                 "db_bytes_per_launch": w["db_bytes"], "hbm_gbs_algorithmic": w["db_bytes"] / kernel_ms / 1e6,
-                "traffic": traffic, "n_slices": w["n_slices"], "grid": w["grid"], "variant": w["variant"]}
+                "traffic": measured_traffic(world),
+                "traffic_note": "dram bytes per launch from an ncu --set full capture of this N (profiles/roofline_traffic.json); "
+                                "null = no capture at this N",
+                "n_slices": w["n_slices"], "grid": w["grid"], "variant": w["variant"]}
 
-    # recall of the bf16 engine against a torch fp32 matmul on a query subsample (rank-local rows -> global merge
-    # is already done by the engine, so gather the reference over all ranks' rows)
-    nchk = 64
-    qs = xq[:nchk].float()
-    best_v = torch.full((nchk, a.k), -float("inf"), device=dev)
-    best_i = torch.full((nchk, a.k), -1, dtype=torch.int64, device=dev)
-    for r0 in range(0, hi - lo, 1 << 20):
-        blk = xb[r0:r0 + (1 << 20)].float()
-        s = qs @ blk.T
-        if a.metric == "l2":
-            s = -((qs * qs).sum(1)[:, None] - 2 * s + (blk * blk).sum(1)[None, :])
-        v, i = torch.topk(s, min(a.k, blk.shape[0]), dim=1)
-        cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i + r0 + lo], 1)
-        o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :a.k]
-        best_v, best_i = torch.gather(cv, 1, o), torch.gather(ci, 1, o)
-    if world > 1:
-        gv = [torch.empty_like(best_v) for _ in range(world)]
-        gi = [torch.empty_like(best_i) for _ in range(world)]
-        dist.all_gather(gv, best_v)
-        dist.all_gather(gi, best_i)
-        cv, ci = torch.cat(gv, 1), torch.cat(gi, 1)
-        o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :a.k]
-        best_i = torch.gather(ci, 1, o)
-    ref_i = best_i.cpu().numpy()
-    got_i = torch.as_tensor(I)[:nchk].cpu().numpy()
-    recall = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, ref_i)]))
+    # ---- check of a query subsample against torch fp32: (i) on the same bf16 values (isolates the kernel: full
+    # id/score comparison up to ties), (ii) on the unrounded fp32 inputs (north_star's recall@10 >= 0.99)
+    nchk = min(a.check_queries, a.nq)
+    sel = torch.arange(0, a.nq, max(1, a.nq // nchk), device=dev)[:nchk]
+    ref = TorchRef(torch, dist, world, dev, a.k, a.metric)
+    D_ref, I_ref = ref.topk(xq[sel].float(), ((lo + r0, xb[r0:r0 + (1 << 20)].float()) for r0 in range(0, hi - lo, 1 << 20)))
+    got_d, got_i = torch.as_tensor(D)[sel].cpu().numpy(), torch.as_tensor(I)[sel].cpu().numpy()
+    recall = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, I_ref)]))
+    beyond_tie = count_beyond_tie(got_d, got_i, D_ref, I_ref, 2e-5)
+    max_dd = float(np.max(np.abs(got_d - D_ref)))
+    qs32 = xq32[sel] if xq32 is not None else gen_rows(torch, dev, Q_SEED, 0, a.nq, a.dim, torch.float32)[sel]
+    _, I32 = ref.topk(qs32, ((r0, gen_rows(torch, dev, DB_SEED, r0, min(hi, r0 + (1 << 20)), a.dim, torch.float32, centres))
+                             for r0 in range(lo, hi, 1 << 20)))
+    recall32 = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, I32)]))
+    same_e2e = bool(np.array_equal(torch.as_tensor(Ih)[sel.cpu()].cpu().numpy(), got_i))
+    check = {"queries_checked": int(nchk), "reference": "torch fp32 matmul + topk over all rows (all ranks)",
+             "recall_at_k_same_bf16_values": recall, "mismatch_beyond_tie_2e-5": beyond_tie,
+             "max_abs_score_diff": max_dd, "recall_at_k_vs_unrounded_fp32_inputs": recall32,
+             "e2e_ids_equal_device_ids": same_e2e}
 
-    # the same against fp32 scores of the UNROUNDED fp32 rows and queries (regenerated chunk by chunk)
-    qs32 = xq32[:nchk] if xq32 is not None else gen_rows(torch, dev, Q_SEED, 0, nchk, a.dim, torch.float32)
-    bv = torch.full((nchk, a.k), -float("inf"), device=dev)
-    bi = torch.full((nchk, a.k), -1, dtype=torch.int64, device=dev)
-    for r0 in range(lo, hi, 1 << 20):
-        blk = gen_rows(torch, dev, DB_SEED, r0, min(hi, r0 + (1 << 20)), a.dim, torch.float32, centres)
-        s = qs32 @ blk.T
-        if a.metric == "l2":
-            s = -((qs32 * qs32).sum(1)[:, None] - 2 * s + (blk * blk).sum(1)[None, :])
-        v, i = torch.topk(s, min(a.k, blk.shape[0]), dim=1)
-        cv, ci = torch.cat([bv, v], 1), torch.cat([bi, i + r0], 1)
-        o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :a.k]
-        bv, bi = torch.gather(cv, 1, o), torch.gather(ci, 1, o)
+    # ------------------------------------------------------------------ the other BASELINE.json configs
+    configs = []
+
+    def guarded(name, fn):
+        try:
+            r = fn()
+            if r is not None:
+                configs.append(r)
+        except Exception as e:  # a broken side measurement must not take the headline line with it
+            configs.append({"config": name, "error": repr(e)[:300]})
+        torch.cuda.empty_cache()
+        barrier()
+
+    def cfg_mining():
+        """configs[2]: hard-negative mining, one 65 536-anchor chunk (anchors = global rows 0..65535), k=50, the
+        anchor itself and its group of four excluded, against the headline database split over the ranks."""
+        n_anchor, k = 65_536, 50
+        anchors = gen_rows(torch, dev, DB_SEED, 0, n_anchor, a.dim, torch.bfloat16, centres)
+        self_ids = torch.arange(n_anchor, device=dev)
+        gq = (self_ids // 4).to(torch.int32)
+        groups = (torch.arange(lo, hi, device=dev) // 4).to(torch.int32)
+        if world > 1:
+            index.set_groups_local(groups)
+        else:
+            index.set_groups(groups)
+
+        def step():
+            return index.search(anchors, k, self_ids=self_ids, group_q=gq, profile=True)
+        ms, kms_, (Dm, Im) = timed(step, 3, 1, collect_kernel=True)
+        ms /= 3
+        km = float(np.mean(kms_[-3:]))
+        w_ = local.last_work()
+        ok_self = bool((Im != self_ids[:, None]).all())
+        ok_grp = bool(((Im // 4) != (self_ids // 4)[:, None]).all())
+        sub = torch.arange(0, n_anchor, n_anchor // 256, device=dev)[:256]
+        r2 = TorchRef(torch, dist, world, dev, k, a.metric)
+        Dr, Ir = r2.topk(anchors[sub].float(), ((lo + r0, xb[r0:r0 + (1 << 20)].float()) for r0 in range(0, hi - lo, 1 << 20)),
+                         self_ids=self_ids[sub], group_q=gq[sub].long(), group_of=lambda ids: ids // 4)
+        gd, gi = Dm[sub].cpu().numpy(), Im[sub].cpu().numpy()
+        flops_total = 2.0 * n_anchor * a.rows * a.dim
+        per_gpu_tf = w_["flops"] / km / 1e9
+        rows_local = hi - lo
+        return {"config": "configs[2] hard-negative mining chunk", "anchors": n_anchor, "k": k, "rows_total": a.rows,
+                "rows_per_gpu": rows_local, "exclusion": "self + group of 4", "ms_per_chunk": ms, "kernel_ms": km,
+                "anchors_per_s": n_anchor / ms * 1e3, "tflops_whole_job": flops_total / ms / 1e9,
+                "roofline": {"bound": "tensor", "achieved": per_gpu_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": per_gpu_tf / peak_tf, "per": "GPU, kernel time", "variant": w_["variant"],
+                             "kernel_share_of_step": km / ms},
+                "self_excluded": ok_self, "group_excluded": ok_grp,
+                "check_256_anchors_vs_torch_fp32": {"recall": float(np.mean([len(np.intersect1d(x, y)) / k for x, y in zip(gi, Ir)])),
+                                                    "mismatch_beyond_tie_2e-5": count_beyond_tie(gd, gi, Dr, Ir, 2e-5)},
+                "whole_50M_join_estimate_s_on_8_gpus": (50_000_000 / n_anchor) * (ms / 1e3) * (6_250_000 / rows_local),
+                "estimate_note": "chunk time scaled by rows to the 6.25M-row shard of configs[2] x 763 chunks; full 2*N^2*d count"}
+
+    def cfg_latency():
+        """configs[4]: small-batch latency against lat_rows rows PER rank (100M x 768 over 8 GPUs = 12.5M each):
+        >= 200 DISTINCT query batches per size, per-call device time (CUDA events) and wall time (with a
+        synchronize per call, what a caller sees), p50 / p99, max over ranks."""
+        have = hi - lo
+        extra = a.lat_rows - have
+        if extra > 0:
+            for r0 in range(0, extra, 1 << 20):
+                blk = gen_rows(torch, dev, LAT_SEED + rank * 4096, r0, min(extra, r0 + (1 << 20)), a.dim, torch.bfloat16)
+                (index.add_local if world > 1 else index.add)(blk)
+        rows_local = int(local.ntotal)
+        out = {"config": "configs[4] small-batch latency", "rows_per_gpu": rows_local, "rows_total": rows_local * world,
+               "k": a.k, "batches_per_size": 200, "sizes": []}
+        for nq in (1, 16, 64):
+            n_b = 200
+            qs = gen_rows(torch, dev, Q_SEED + 31, 0, n_b * nq, a.dim, torch.bfloat16)
+            for b in range(5):
+                index.search(qs[b * nq:(b + 1) * nq], a.k)
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_b)]
+            wall = []
+            local.profile_ms()
+            for b in range(n_b):
+                q = qs[b * nq:(b + 1) * nq]
+                t0 = time.perf_counter()
+                ev[b][0].record()
+                index.search(q, a.k, profile=True)
+                ev[b][1].record()
+                torch.cuda.synchronize()
+                wall.append((time.perf_counter() - t0) * 1e3)
+            gpu = [e0.elapsed_time(e1) for e0, e1 in ev]
+            kk = local.profile_ms()
+            kern = float(np.median(kk)) if kk else float("nan")
+            w_ = local.last_work()
+            gbs = w_["db_bytes"] / kern / 1e6
+            out["sizes"].append({
+                "nq": nq, "gpu_ms_p50": max_over_ranks(np.percentile(gpu, 50)), "gpu_ms_p99": max_over_ranks(np.percentile(gpu, 99)),
+                "wall_ms_p50": max_over_ranks(np.percentile(wall, 50)), "wall_ms_p99": max_over_ranks(np.percentile(wall, 99)),
+                "qps_at_wall_p50": nq / max_over_ranks(np.percentile(wall, 50)) * 1e3, "kernel_ms_median": kern,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": w_["db_bytes"], "variant": w_["variant"],
+                             "frac_of_call_wall_p50": w_["db_bytes"] / np.percentile(wall, 50) / 1e6 / peaks["hbm_gbs"]}})
+        return out
+
+    def cfg_kmeans():
+        """configs[3]: one Lloyd iteration (fused-kernel k=1 assignment + scatter-add update + all-reduce + finalize)
+        over km_points x 384 bf16 points split over the ranks, 65 536 centroids."""
+        d, K = 384, 65_536
+        plo, phi = shard_bounds(a.km_points, world, rank)
+        pts = gen_rows(torch, dev, KM_SEED, plo, phi, d, torch.bfloat16)
+        km = Kmeans(d, K, niter=1, seed=42, storage="bf16", device=local_rank)
+        km.centroids = gen_rows(torch, dev, KM_SEED, 0, K, d, torch.float32).contiguous()   # the first K points
+        km.step(pts)                                                                        # warm-up
+        barrier()
+        times, phases = [], []
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            km.step(pts, profile=True)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(max_over_ranks(e0.elapsed_time(e1)))
+            phases.append(km.last_timing)
+            barrier()
+        ms = float(np.mean(times))
+        # agreement of the assignment with torch fp32 on a subsample (centroids as the kernel sees them: bf16)
+        sub = torch.arange(0, phi - plo, max(1, (phi - plo) // 4096), device=dev)[:4096]
+        km._set_centroids(km.centroids)
+        a_sub, _ = km._index.assign(pts[sub])
+        c = km.centroids.bfloat16().float()
+        xs = pts[sub].float()
+        d2 = (xs * xs).sum(1)[:, None] - 2 * xs @ c.T + (c * c).sum(1)[None, :]
+        refa = d2.argmin(1)
+        differ = refa != a_sub.long()
+        gap = float((d2[differ, a_sub.long()[differ]] - d2[differ, refa[differ]]).abs().max()) if bool(differ.any()) else 0.0
+        flops_gpu = 2.0 * (phi - plo) * K * d
+        tf = flops_gpu / ms / 1e9
+        tf_assign = flops_gpu / float(np.mean([p["assign_ms"] for p in phases])) / 1e9
+        res = {"config": "configs[3] k-means iteration", "points_total": a.km_points, "points_per_gpu": phi - plo, "d": d, "K": K,
+               "ms_per_iteration": ms, "iterations_per_s": 1e3 / ms,
+               "phases_ms": {k_: float(np.mean([p[k_] for p in phases])) for k_ in phases[0]},
+               "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                            "per": "GPU, whole iteration (assign + update + all-reduce + finalize)",
+                            "assign_only_tflops": tf_assign, "assign_only_frac": tf_assign / peak_tf},
+               "assign_agreement_4096_points_vs_torch_fp32": float((~differ).float().mean()),
+               "largest_distance_gap_among_disagreements": gap,
+               "nonempty_clusters": int((km.last_counts > 0).sum())}
+        del pts
+        return res
+
+    def cfg_exact():
+        """configs[0]: exact top-10 IP, 100k x 384 fp32 database, 10k fp32 queries (three bf16 planes, six plane
+        products on the tensor cores, fp32 rescoring).  Every rank runs a replica; rank 0 reports."""
+        n, d, nq, k = 100_000, 384, 10_000, 10
+        xb0 = gen_rows(torch, dev, DB_SEED, 0, n, d, torch.float32)
+        xq0 = gen_rows(torch, dev, Q_SEED, 0, nq, d, torch.float32)
+        ex = IndexFlat(d, "ip", "exact", device=local_rank)
+        ex.add(xb0)
+        for _ in range(3):
+            ex.search(xq0, k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            De, Ie = ex.search(xq0, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        bad, maxd, diff_ids = 0, 0.0, 0
+        for q0 in range(0, nq, 2048):
+            s = xq0[q0:q0 + 2048] @ xb0.T
+            v, i = torch.topk(s, k, dim=1)
+            gd, gi = De[q0:q0 + 2048].cpu().numpy(), Ie[q0:q0 + 2048].cpu().numpy()
+            bad += count_beyond_tie(gd, gi, v.cpu().numpy(), i.cpu().numpy(), 1e-5)
+            diff_ids += int((gi != i.cpu().numpy()).sum())
+            maxd = max(maxd, float((De[q0:q0 + 2048] - v).abs().max()))
+        ex.close()
+        tf = 2.0 * nq * n * d / ms / 1e9
+        return {"config": "configs[0] exact fp32 search", "rows": n, "d": d, "queries": nq, "k": k, "ms_per_batch": ms,
+                "queries_per_s": nq / ms * 1e3,
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                             "note": "algorithmic 2*nq*N*d count; the exact mode issues 6 bf16 plane products per score, so the "
+                                     "tensor pipe does 6x this; the batch is 4 ms of work (launch- and tail-bound)",
+                             "mma_tflops": 6 * tf},
+                "check_all_10k_queries_vs_torch_fp32": {"ids_differing": diff_ids, "mismatch_beyond_tie_1e-5": bad,
+                                                         "max_abs_score_diff": maxd}}
+
+    def cfg_ingest():
+        """Host -> HBM add() rate: 2 GB of fp32 rows from pageable memory (host threads copy
+        into two pinned 64 MB staging buffers while the previous chunk is on PCIe and the one before is packed) and
+        from memory the caller pinned."""
+        if world > 1 or rank != 0:
+            return None
+        n, d = 650_000, 768
+        x = np.empty((n, d), np.float32)
+        tile = np.random.default_rng(3).standard_normal((8192, d), dtype=np.float32)
+        for r0 in range(0, n, 8192):
+            x[r0:r0 + 8192] = tile[:min(8192, n - r0)]
+        ing = IndexFlat(d, "ip", "bf16", device=local_rank)
+        ing.reserve(n)
+        res = {"config": "ingest (host -> HBM add)", "rows": n, "d": d, "bytes": int(x.nbytes)}
+        for name, src in (("pageable_fp32", x), ("pinned_fp32", torch.from_numpy(x).pin_memory())):
+            ing.reset()
+            ing.add(src[:70_000])            # first call allocates the staging buffers
+            ing.reset()
+            t0 = time.perf_counter()
+            ing.add(src)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            res[name + "_gbs"] = x.nbytes / dt / 1e9
+        ing.close()
+        return res
+
+    if "2" in which:
+        guarded("configs[2]", cfg_mining)
+    if "4" in which:
+        guarded("configs[4]", cfg_latency)
+    # the headline database is no longer needed: free it before the 76.8 GB k-means matrix
+    del xb
     if world > 1:
-        gv = [torch.empty_like(bv) for _ in range(world)]
-        gi = [torch.empty_like(bi) for _ in range(world)]
-        dist.all_gather(gv, bv)
-        dist.all_gather(gi, bi)
-        cv, ci = torch.cat(gv, 1), torch.cat(gi, 1)
-        o = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :a.k]
-        bi = torch.gather(ci, 1, o)
-    recall32 = float(np.mean([len(np.intersect1d(x, y)) / a.k for x, y in zip(got_i, bi.cpu().numpy())]))
-    same_e2e = bool(np.array_equal(torch.as_tensor(Ih)[:nchk].cpu().numpy(), got_i))
+        index.local.close()
+    else:
+        index.close()
+    torch.cuda.empty_cache()
+    if "3" in which:
+        guarded("configs[3]", cfg_kmeans)
+    if "0" in which:
+        guarded("configs[0]", cfg_exact)
+    if "ingest" in which:
+        guarded("ingest", cfg_ingest)
 
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -400,9 +675,11 @@ def run_ours(a):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_base,
+            "check": check,
             "recall_at_k_vs_fp32_torch_on_same_bf16_values": recall,
             "recall_at_k_vs_fp32_torch_on_unrounded_fp32_inputs": recall32,
             "clocks": clocks,
+            "configs": configs,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

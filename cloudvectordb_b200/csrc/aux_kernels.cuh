@@ -36,17 +36,23 @@ __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 //                   database row: bf16 split of -|x|^2/2 ; query row: 1, 1, 1
 //   norms[r] = |x|^2 of the values actually stored (optional).
 // ---------------------------------------------------------------------------
+// Rows n .. n_pad-1 of `out` are written as zeros (query matrices are padded to whole tiles so that the
+// A-operand TMA boxes never run out of bounds).
 template <typename Tin>
-__global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, int64_t in_stride,
+__global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int64_t n_pad, int d, int64_t in_stride,
                                  __nv_bfloat16* __restrict__ out, int Kp, int planes, int l2, int is_query,
                                  float* __restrict__ norms, unsigned long long* __restrict__ bad_rows) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int row_elems = planes * Kp;
-    for (int64_t r = warp0; r < n; r += nwarps) {
-        const Tin* src = in + r * in_stride;
+    for (int64_t r = warp0; r < n_pad; r += nwarps) {
         __nv_bfloat16* dst = out + r * row_elems;
+        if (r >= n) {
+            for (int c = lane; c < row_elems; c += 32) dst[c] = __float2bfloat16_rn(0.f);
+            continue;
+        }
+        const Tin* src = in + r * in_stride;
         float nrm = 0.f;
         for (int c = lane; c < Kp; c += 32) {
             float x = c < d ? to_f32(src[c]) : 0.f;
@@ -90,21 +96,29 @@ __global__ void pack_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, i
 }
 
 // ---------------------------------------------------------------------------
-// merge_partials: final k-way merge of the per-slice (or per-probe) lists of one
-// query, one warp per query, keys -> (D, I).
-//   IP: D = score.            L2: D = |q|^2 - 2*score (squared distance).
-//   Missing results: I = -1, D = -inf (IP) / +inf (L2).
+// merge_partials: final k-way merge of the per-slice (or per-probe, or per-rank)
+// lists of one query, one warp per query.  List l of query q starts at
+// part[q * q_stride + l * l_stride] and holds k_in keys.
+//   KEYS_OUT = false: keys -> (D, I).  IP: D = score.  L2: D = |q|^2 - 2*score
+//                     (squared distance).  Missing results: I = -1, D = -inf (IP) / +inf (L2).
+//   KEYS_OUT = true : keys -> keys_out[q][k] with the id rewritten to the caller's id
+//                     (row_ids translation, + id_base); missing results are key 0.  This is what
+//                     ranks exchange in a sharded search: 8 bytes per candidate, still sorted, still
+//                     mergeable by this same kernel.
+// row_ids (optional): caller-visible id of stored row r for r < row_ids_n (an index whose rows were
+// re-stored list-major keeps returning the ids the rows were added under).
 // Every list is sorted descending with its empty slots (key 0) at the end, so
 // this is a head-pointer merge: lane l owns lists l, l+32, ...; per output rank
 // each lane offers the best head among its lists, the warp picks the largest
 // and the owning lane advances that head.  Cost per query: k * n_lists / 32
-// loads per lane (the old "rescan everything per rank" cost k * n_lists * k / 32).
+// loads per lane.
 // Dynamic shared memory: blockDim.x/32 * n_lists uint16 head positions.
 // ---------------------------------------------------------------------------
-template <typename Tidx>
+template <typename Tidx, bool KEYS_OUT>
 __global__ void merge_partials_kernel(const uint64_t* __restrict__ part, int64_t nq, int n_lists, int k_in, int k, int l2,
-                                      const float* __restrict__ qnorm, int64_t id_base, float* __restrict__ D,
-                                      Tidx* __restrict__ I) {
+                                      const float* __restrict__ qnorm, int64_t id_base, int64_t q_stride,
+                                      int64_t l_stride, const int32_t* __restrict__ row_ids, int64_t row_ids_n,
+                                      float* __restrict__ D, Tidx* __restrict__ I, uint64_t* __restrict__ keys_out) {
     extern __shared__ uint16_t s_heads[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -113,30 +127,41 @@ __global__ void merge_partials_kernel(const uint64_t* __restrict__ part, int64_t
     uint16_t* head = s_heads + static_cast<size_t>(wib) * n_lists;
     for (int l = lane; l < n_lists; l += 32) head[l] = 0;
     __syncwarp();
-    const uint64_t* c = part + q * static_cast<int64_t>(n_lists) * k_in;
+    const uint64_t* c = part + q * q_stride;
     for (int r = 0; r < k; ++r) {
         uint64_t best = 0;
         int bl = -1;
         for (int l = lane; l < n_lists; l += 32) {
             const int h = head[l];
             if (h < k_in) {
-                const uint64_t key = c[static_cast<int64_t>(l) * k_in + h];
+                const uint64_t key = c[static_cast<int64_t>(l) * l_stride + h];
                 if (key > best) { best = key; bl = l; }
             }
         }
         const uint64_t win = warp_max_u64(best);
         if (win == 0) {  // every list is exhausted: pad the rest
             for (int rr = r + lane; rr < k; rr += 32) {
-                D[q * k + rr] = l2 ? INFINITY : -INFINITY;
-                I[q * k + rr] = static_cast<Tidx>(-1);
+                if constexpr (KEYS_OUT) {
+                    keys_out[q * k + rr] = 0;
+                } else {
+                    D[q * k + rr] = l2 ? INFINITY : -INFINITY;
+                    I[q * k + rr] = static_cast<Tidx>(-1);
+                }
             }
             break;
         }
         if (best == win) {  // keys are unique (distinct rows): exactly one lane holds the winner
             head[bl] = static_cast<uint16_t>(head[bl] + 1);
-            const float s = key_score(win);
-            D[q * k + r] = l2 ? (qnorm[q] - 2.f * s) : s;
-            I[q * k + r] = static_cast<Tidx>(static_cast<int64_t>(key_row(win)) + id_base);
+            const uint32_t row = key_row(win);
+            const int64_t id = ((row_ids != nullptr && row < row_ids_n) ? static_cast<int64_t>(row_ids[row])
+                                                                         : static_cast<int64_t>(row)) + id_base;
+            if constexpr (KEYS_OUT) {
+                keys_out[q * k + r] = (win & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(~static_cast<uint32_t>(id));
+            } else {
+                const float s = key_score(win);
+                D[q * k + r] = l2 ? (qnorm[q] - 2.f * s) : s;
+                I[q * k + r] = static_cast<Tidx>(id);
+            }
         }
         __syncwarp();
     }

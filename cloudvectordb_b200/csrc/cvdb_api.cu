@@ -14,6 +14,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#ifdef __linux__
+#include <sched.h>
+#endif
+#include <vector>
 
 #include "aux_kernels.cuh"
 #include "launchers.h"
@@ -151,6 +156,35 @@ struct Index {
     DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
     DevBuf bad_rows;  // one uint64: rows (added or queried) whose squared norm was not finite
     bool has_groups = false;
+    // Rows re-stored list-major keep their caller-visible ids in row_ids: every id leaving the library is
+    // translated through it, and everything indexed by STORED POSITION (groups, self exclusion, export,
+    // truncate) is refused while the index is in this state.
+    bool permuted() const { return row_ids_n > 0; }
+
+    // Tensor maps of the last launch, keyed by what they describe (encoding one costs microseconds of host time
+    // on the small-batch path).
+    struct TmapSlot {
+        const void* base = nullptr;
+        int64_t rows = -1;
+        int row_elems = 0, box_rows = 0;
+        CUtensorMap map;
+    };
+    TmapSlot tm_q, tm_x, tm_q_ivf, tm_x_ivf;
+
+    // The scratch buffers above are per handle: a call on another stream than the previous one first waits for
+    // the previous call's work (event recorded at the end of every call).
+    cudaEvent_t done_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+
+    // host->device ingest: two pinned staging buffers + two device staging buffers, so the copy of chunk
+    // i+1 overlaps the packing kernel of chunk i
+    void* pin[2] = {nullptr, nullptr};
+    size_t pin_cap = 0;
+    cudaEvent_t pin_free[2] = {nullptr, nullptr};  // the H2D copy out of pin[b] has finished
+    DevBuf stage2[2];
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};  // the packing kernel reading stage2[b] has finished
+    cudaStream_t copy_stream = nullptr;
 
     // ring of event pairs bracketing profiled GEMM+top-k launches (opts.profile)
     static constexpr int kProfSlots = 64;
@@ -169,6 +203,49 @@ struct cvdb_guard {
         else prev = -1;
     }
     ~cvdb_guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Orders a call on `st` after the previous call on this handle when that one ran on another stream.
+struct StreamOrder {
+    Index* ix;
+    cudaStream_t st;
+    StreamOrder(Index* ix_, cudaStream_t st_) : ix(ix_), st(st_) {
+        if (ix->has_last && ix->last_stream != st && ix->done_ev) cudaStreamWaitEvent(st, ix->done_ev, 0);
+    }
+    ~StreamOrder() {
+        if (!ix->done_ev && cudaEventCreateWithFlags(&ix->done_ev, cudaEventDisableTiming) != cudaSuccess) {
+            ix->done_ev = nullptr;
+            return;
+        }
+        if (cudaEventRecord(ix->done_ev, st) == cudaSuccess) {
+            ix->last_stream = st;
+            ix->has_last = true;
+        }
+    }
+};
+
+// The handle-less entry points (k-means update, merges, triplets) take raw device pointers: run them on the
+// device that owns the data, whatever the caller's current device is.
+int device_of(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+struct ptr_guard {
+    int prev = -1;
+    explicit ptr_guard(const void* p) {
+        const int dev = device_of(p);
+        if (dev < 0) return;
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~ptr_guard() {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
@@ -198,26 +275,154 @@ int grow(Index* ix, int64_t need, cudaStream_t st) {
 }
 
 template <typename Tin>
-void launch_pack(const Tin* in, int64_t n, int d, __nv_bfloat16* out, const Index* ix, int is_query, float* norms,
-                 cudaStream_t st) {
+void launch_pack(const Tin* in, int64_t n, int64_t n_pad, int d, __nv_bfloat16* out, const Index* ix, int is_query,
+                 float* norms, cudaStream_t st) {
     const int threads = 256;
-    const int64_t blocks = std::min<int64_t>(ceil_div(n, threads / 32), 148 * 32);
-    pack_rows_kernel<Tin><<<static_cast<unsigned>(blocks), threads, 0, st>>>(in, n, d, d, out, ix->Kp, ix->planes,
+    const int64_t blocks = std::min<int64_t>(ceil_div(n_pad, threads / 32), 148 * 32);
+    pack_rows_kernel<Tin><<<static_cast<unsigned>(blocks), threads, 0, st>>>(in, n, n_pad, d, d, out, ix->Kp, ix->planes,
                                                                                 ix->metric == CVDB_METRIC_L2, is_query, norms,
                                                                                 static_cast<unsigned long long*>(ix->bad_rows.p));
     ++g_launches;
 }
 
+// n rows of `in` -> packed rows of `out`; rows n .. n_pad-1 of `out` become zeros
 int pack_dispatch(const void* in, int dtype, int64_t n, __nv_bfloat16* out, const Index* ix, int is_query, float* norms,
-                  cudaStream_t st) {
-    if (n == 0) return CVDB_OK;
+                  cudaStream_t st, int64_t n_pad = 0) {
+    n_pad = std::max(n_pad, n);
+    if (n_pad == 0) return CVDB_OK;
     if (dtype == CVDB_DTYPE_F32)
-        launch_pack<float>(static_cast<const float*>(in), n, ix->d, out, ix, is_query, norms, st);
+        launch_pack<float>(static_cast<const float*>(in), n, n_pad, ix->d, out, ix, is_query, norms, st);
     else if (dtype == CVDB_DTYPE_F16)
-        launch_pack<__half>(static_cast<const __half*>(in), n, ix->d, out, ix, is_query, norms, st);
+        launch_pack<__half>(static_cast<const __half*>(in), n, n_pad, ix->d, out, ix, is_query, norms, st);
     else
-        launch_pack<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(in), n, ix->d, out, ix, is_query, norms, st);
+        launch_pack<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(in), n, n_pad, ix->d, out, ix, is_query, norms, st);
     CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+int get_tmap(Index::TmapSlot& s, CUtensorMap* out, const void* base, int64_t rows, int row_elems, int box_rows) {
+    if (s.base != base || s.rows != rows || s.row_elems != row_elems || s.box_rows != box_rows) {
+        TRY(make_tmap_2d(&s.map, base, rows, row_elems, box_rows));
+        s.base = base;
+        s.rows = rows;
+        s.row_elems = row_elems;
+        s.box_rows = box_rows;
+    }
+    *out = s.map;
+    return CVDB_OK;
+}
+
+// final merge of `n_lists` sorted key lists per query -> (D, I) or rewritten keys (see merge_partials_kernel)
+int launch_merge(const uint64_t* part, int64_t nq, int n_lists, int k_in, int k, int l2, const float* qnorm,
+                 int64_t id_base, int64_t q_stride, int64_t l_stride, const int32_t* row_ids, int64_t row_ids_n, float* D,
+                 int64_t* I64, int32_t* I32, uint64_t* keys_out, cudaStream_t st) {
+    const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
+    const size_t smem = 8 * static_cast<size_t>(n_lists) * sizeof(uint16_t);
+    if (keys_out)
+        merge_partials_kernel<int64_t, true><<<blocks, 256, smem, st>>>(part, nq, n_lists, k_in, k, l2, qnorm, id_base, q_stride,
+                                                                         l_stride, row_ids, row_ids_n, nullptr, nullptr, keys_out);
+    else if (I64)
+        merge_partials_kernel<int64_t, false><<<blocks, 256, smem, st>>>(part, nq, n_lists, k_in, k, l2, qnorm, id_base, q_stride,
+                                                                          l_stride, row_ids, row_ids_n, D, I64, nullptr);
+    else
+        merge_partials_kernel<int32_t, false><<<blocks, 256, smem, st>>>(part, nq, n_lists, k_in, k, l2, qnorm, id_base, q_stride,
+                                                                          l_stride, row_ids, row_ids_n, D, I32, nullptr);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+// ------------------------------------------------------------ host ingest
+constexpr size_t kPinChunk = size_t(64) << 20;  // bytes per pinned staging buffer
+constexpr size_t kSmallAdd = size_t(8) << 20;   // below this an add() is one plain copy
+
+int host_threads() {
+    int n = 0;
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+#endif
+    if (n <= 0) n = static_cast<int>(std::thread::hardware_concurrency());
+    return std::max(1, n);
+}
+
+// memcpy split over a few host threads: one core moves ~10 GB/s, PCIe Gen5 x16 takes ~50
+void parallel_copy(char* dst, const char* src, size_t bytes) {
+    static const int kThreads = std::max(1, std::min(8, host_threads() / 2));
+    const int nt = bytes < (size_t(4) << 20) ? 1 : kThreads;
+    if (nt == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const size_t off = static_cast<size_t>(t) * per;
+        if (off >= bytes) break;
+        th.emplace_back([=] { memcpy(dst + off, src + off, std::min(per, bytes - off)); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : th) t.join();
+}
+
+// n host rows -> packed index rows at `dst`.  Large inputs run as a three-stage pipeline over 64 MB chunks
+// (buffer b = chunk & 1):
+//   host threads   user rows -> pin[b]             once the H2D copy of chunk c-2 has left pin[b]
+//   copy stream    pin[b] -> stage2[b]             once the packing kernel of chunk c-2 is done with stage2[b]
+//   caller stream  stage2[b] -> index rows (pack)  once the copy has landed
+// so the PCIe copy of a chunk overlaps the packing of the previous one and the host memcpy of the next.
+// Memory the caller already pinned (cudaHostAlloc / cudaHostRegister) is copied from directly.
+// Returns after the last row has left host memory (the caller may reuse x) and has been packed.
+int ingest_host_rows(Index* ix, const char* x, int64_t n, int dtype, size_t esz, __nv_bfloat16* dst, cudaStream_t st) {
+    const size_t row_b = static_cast<size_t>(ix->d) * esz;
+    const size_t total = static_cast<size_t>(n) * row_b;
+    if (total <= kSmallAdd) {
+        TRY(ix->stage_in.ensure(total));
+        CU_TRY(cudaMemcpyAsync(ix->stage_in.p, x, total, cudaMemcpyHostToDevice, st));
+        TRY(pack_dispatch(ix->stage_in.p, dtype, n, dst, ix, 0, nullptr, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        return CVDB_OK;
+    }
+    cudaPointerAttributes attr{};
+    const bool src_pinned = cudaPointerGetAttributes(&attr, x) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // unregistered host memory is reported as an error by older runtimes
+    const int64_t chunk_rows = std::max<int64_t>(1, static_cast<int64_t>(kPinChunk / row_b));
+    const size_t chunk_b = static_cast<size_t>(chunk_rows) * row_b;
+    if (!ix->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        if (!ix->pin_free[b]) CU_TRY(cudaEventCreateWithFlags(&ix->pin_free[b], cudaEventDisableTiming));
+        if (!ix->stage_free[b]) CU_TRY(cudaEventCreateWithFlags(&ix->stage_free[b], cudaEventDisableTiming));
+        TRY(ix->stage2[b].ensure(chunk_b));
+    }
+    if (!src_pinned && ix->pin_cap < chunk_b) {
+        for (int b = 0; b < 2; ++b) {
+            if (ix->pin[b]) cudaFreeHost(ix->pin[b]);
+            ix->pin[b] = nullptr;
+        }
+        ix->pin_cap = 0;
+        for (int b = 0; b < 2; ++b) CU_TRY(cudaHostAlloc(&ix->pin[b], chunk_b, cudaHostAllocDefault));
+        ix->pin_cap = chunk_b;
+    }
+    int64_t c = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t m = std::min(chunk_rows, n - r0);
+        const size_t bytes = static_cast<size_t>(m) * row_b;
+        const char* src = x + static_cast<size_t>(r0) * row_b;
+        if (!src_pinned) {
+            if (c >= 2) CU_TRY(cudaEventSynchronize(ix->pin_free[b]));
+            parallel_copy(static_cast<char*>(ix->pin[b]), src, bytes);
+            src = static_cast<const char*>(ix->pin[b]);
+        }
+        if (c >= 2) CU_TRY(cudaStreamWaitEvent(ix->copy_stream, ix->stage_free[b], 0));
+        CU_TRY(cudaMemcpyAsync(ix->stage2[b].p, src, bytes, cudaMemcpyHostToDevice, ix->copy_stream));
+        CU_TRY(cudaEventRecord(ix->pin_free[b], ix->copy_stream));
+        CU_TRY(cudaStreamWaitEvent(st, ix->pin_free[b], 0));
+        TRY(pack_dispatch(ix->stage2[b].p, dtype, m, dst + r0 * ix->row_elems, ix, 0, nullptr, st));
+        CU_TRY(cudaEventRecord(ix->stage_free[b], st));
+    }
+    CU_TRY(cudaStreamSynchronize(ix->copy_stream));
+    CU_TRY(cudaStreamSynchronize(st));
     return CVDB_OK;
 }
 
@@ -286,8 +491,11 @@ void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& 
 
 // Core: search `nq` packed-on-the-fly queries against the whole index.
 // Outputs are device pointers: D [nq][k] f32 and either I64 or I32 [nq][k].
+// `keys_out` (optional, instead of D/I): the merged top-k as keys carrying the caller's ids (shard exchange).
+// `q_norm`: where the squared norms of the packed queries go ([nq] f32, device).
 int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, float* D, int64_t* I64, int32_t* I32,
-                  const int32_t* self_ids, const int32_t* group_q, const cvdb_search_opts* opts, cudaStream_t st) {
+                  const int32_t* self_ids, const int32_t* group_q, const cvdb_search_opts* opts, cudaStream_t st,
+                  uint64_t* keys_out = nullptr, float* q_norm = nullptr) {
     const int E = pick_E(k);
     const int C = 32 * (E ? E : 1);
     const int l2 = ix->metric == CVDB_METRIC_L2;
@@ -297,26 +505,19 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     // TMA boxes never run out of bounds (partially out-of-bounds boxes load measurably slower)
     const int64_t nq_pad = ceil_div(nq, 256) * 256;
     TRY(ix->q_pack.ensure(static_cast<size_t>(nq_pad) * ix->row_elems * 2));
-    TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
-    TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, ix->q_norm.as<float>(), st));
-    if (nq_pad > nq)
-        CU_TRY(cudaMemsetAsync(ix->q_pack.as<__nv_bfloat16>() + nq * ix->row_elems, 0,
-                               static_cast<size_t>(nq_pad - nq) * ix->row_elems * 2, st));
+    if (!q_norm) {
+        TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
+        q_norm = ix->q_norm.as<float>();
+    }
+    TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, q_norm, st, nq_pad));
+    const int32_t* row_ids = ix->permuted() ? ix->row_ids.as<int32_t>() : nullptr;
 
     if (ix->ntotal == 0) {
         // nothing to search: all padding
         TRY(ix->part.ensure(static_cast<size_t>(nq) * k * 8));
         CU_TRY(cudaMemsetAsync(ix->part.p, 0, static_cast<size_t>(nq) * k * 8, st));
-        const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
-        if (I64)
-            merge_partials_kernel<int64_t><<<blocks, 256, 8 * sizeof(uint16_t), st>>>(
-                ix->part.as<uint64_t>(), nq, 1, k, k, l2, ix->q_norm.as<float>(), id_base, D, I64);
-        else
-            merge_partials_kernel<int32_t><<<blocks, 256, 8 * sizeof(uint16_t), st>>>(
-                ix->part.as<uint64_t>(), nq, 1, k, k, l2, ix->q_norm.as<float>(), id_base, D, I32);
-        ++g_launches;
-        CU_TRY(cudaGetLastError());
-        return CVDB_OK;
+        return launch_merge(ix->part.as<uint64_t>(), nq, 1, k, k, l2, q_norm, id_base, k, k, nullptr, 0, D, I64, I32,
+                            keys_out, st);
     }
 
     GemmTopkParams p{};
@@ -395,22 +596,21 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     TRY(ix->part.ensure(static_cast<size_t>(nq) * p.n_slices * k * 8));
     p.cand = ix->cand.as<uint64_t>();
     p.part = ix->part.as<uint64_t>();
-    TRY(ix->gthr.ensure(static_cast<size_t>(nq) * 4));
-    CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq) * 4, st));
-    p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
     {
+        // shared thresholds [nq] and wave counters [n_waves] live in one buffer: one memset per launch
         const int64_t n_waves = ceil_div(n_items, std::min<int64_t>(workers, n_items));
-        TRY(ix->waves.ensure(static_cast<size_t>(n_waves) * 4));
-        CU_TRY(cudaMemsetAsync(ix->waves.p, 0, static_cast<size_t>(n_waves) * 4, st));
-        p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->waves.as<uint32_t>();
+        TRY(ix->gthr.ensure(static_cast<size_t>(nq + n_waves) * 4));
+        CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq + n_waves) * 4, st));
+        p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
+        p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->gthr.as<uint32_t>() + nq;
     }
 
     // a single partial query tile on the single-CTA kernel (small, HBM-bound batches): give every epilogue warp a
     // quarter of the queries instead of filling the TMEM lanes from 0 up, where 32 queries are one warp's work
     p.a_quarter = (variant == 1 && nq < 128 && !(opts && (opts->debug_flags & 64))) ? static_cast<int>(ceil_div(nq, 4)) : 0;
     CUtensorMap tq, tx;
-    TRY(make_tmap_2d(&tq, ix->q_pack.p, nq_pad, ix->row_elems, p.a_quarter > 0 ? 32 : 128));
-    TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
+    TRY(get_tmap(ix->tm_q, &tq, ix->q_pack.p, nq_pad, ix->row_elems, p.a_quarter > 0 ? 32 : 128));
+    TRY(get_tmap(ix->tm_x, &tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;
     const int slot = ix->prof_head;
@@ -442,17 +642,10 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     ix->last_grid = grid;
     ix->last_variant = variant;
 
-    const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
-    if (I64)
-        merge_partials_kernel<int64_t><<<blocks, 256, 8 * p.n_slices * sizeof(uint16_t), st>>>(
-            p.part, nq, p.n_slices, k, k, l2, ix->q_norm.as<float>(), id_base, D, I64);
-    else
-        merge_partials_kernel<int32_t><<<blocks, 256, 8 * p.n_slices * sizeof(uint16_t), st>>>(
-            p.part, nq, p.n_slices, k, k, l2, ix->q_norm.as<float>(), id_base, D, I32);
-    ++g_launches;
-    CU_TRY(cudaGetLastError());
+    TRY(launch_merge(p.part, nq, p.n_slices, k, k, l2, q_norm, id_base, static_cast<int64_t>(p.n_slices) * k, k, row_ids,
+                     ix->row_ids_n, D, I64, I32, keys_out, st));
 
-    if (ix->planes == 3 && D != nullptr) {
+    if (ix->planes == 3 && D != nullptr && !keys_out) {
         const unsigned rb = static_cast<unsigned>(ceil_div(nq * k, 8));
         if (I64)
             rescore_exact_kernel<int64_t><<<rb, 256, 0, st>>>(ix->q_pack.as<__nv_bfloat16>(), ix->x, nq, k, ix->d, ix->Kp,
@@ -545,20 +738,17 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
         p.part = ix->part.as<uint64_t>();
         p.gthr = ix->gthr.as<uint32_t>();
         CUtensorMap tq, tx;
-        TRY(make_tmap_2d(&tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 32));  // four 32-row boxes per A tile
-        TRY(make_tmap_2d(&tx, ix->x, ix->ntotal, ix->row_elems, kGroupedBlockN));
+        TRY(get_tmap(ix->tm_q_ivf, &tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 32));  // four 32-row boxes per A tile
+        TRY(get_tmap(ix->tm_x_ivf, &tx, ix->x, ix->ntotal, ix->row_elems, kGroupedBlockN));
         LAUNCH(launch_grouped(E, tq, tx, p, grid, st));
     }
     ix->last_flops = 0;
     ix->last_slices = nprobe;
     ix->last_grid = n_items;
     ix->last_variant = 5;
-    const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
-    merge_partials_kernel<int64_t><<<blocks, 256, 8 * nprobe * sizeof(uint16_t), st>>>(
-        ix->part.as<uint64_t>(), nq, nprobe, k, k, l2, ix->q_norm.as<float>(), 0, D, I);
-    ++g_launches;
-    CU_TRY(cudaGetLastError());
-    return CVDB_OK;
+    // candidate keys of the list scan already carry the caller's row ids (GroupedParams::row_ids)
+    return launch_merge(ix->part.as<uint64_t>(), nq, nprobe, k, k, l2, ix->q_norm.as<float>(), 0,
+                        static_cast<int64_t>(nprobe) * k, k, nullptr, 0, D, I, nullptr, nullptr, st);
 }
 
 int check_index(cvdb_index_t h) {
@@ -644,6 +834,14 @@ int cvdb_index_destroy(cvdb_index_t h) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
         if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
     }
+    for (int b = 0; b < 2; ++b) {
+        if (ix->pin[b]) cudaFreeHost(ix->pin[b]);
+        if (ix->pin_free[b]) cudaEventDestroy(ix->pin_free[b]);
+        if (ix->stage_free[b]) cudaEventDestroy(ix->stage_free[b]);
+        ix->stage2[b].release();
+    }
+    if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
+    if (ix->done_ev) cudaEventDestroy(ix->done_ev);
     delete ix;
     return CVDB_OK;
 }
@@ -664,8 +862,9 @@ int cvdb_index_truncate(cvdb_index_t h, int64_t n) {
     if (n < 0 || n > ix->ntotal)
         return fail(CVDB_EINVAL, "truncate to %lld rows: the index holds %lld", static_cast<long long>(n),
                     static_cast<long long>(ix->ntotal));
-    if (ix->grouped && n != ix->ntotal)
-        return fail(CVDB_EINVAL, "rows are stored list-major after cvdb_index_group_by_list; the last rows added are not the last rows stored");
+    if (ix->permuted() && n < ix->row_ids_n)
+        return fail(CVDB_EINVAL, "rows are stored list-major after cvdb_index_group_by_list; the last rows added are not "
+                                 "the last rows stored (only rows added since the grouping can be dropped; cvdb_index_reset clears)");
     ix->ntotal = n;
     return CVDB_OK;
 }
@@ -708,19 +907,11 @@ int cvdb_index_add(cvdb_index_t h, const void* x, int64_t n, int dtype, int on_d
     TRY(grow(ix, ix->ntotal + n, st));
     const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     __nv_bfloat16* dst = ix->x + ix->ntotal * ix->row_elems;
+    StreamOrder order(ix, st);
     if (on_device) {
         TRY(pack_dispatch(x, dtype, n, dst, ix, 0, nullptr, st));
     } else {
-        // stage through a bounded device buffer
-        const int64_t chunk = std::max<int64_t>(1, (int64_t(256) << 20) / (int64_t(ix->d) * esz));
-        TRY(ix->stage_in.ensure(static_cast<size_t>(std::min(chunk, n)) * ix->d * esz));
-        for (int64_t r0 = 0; r0 < n; r0 += chunk) {
-            const int64_t m = std::min(chunk, n - r0);
-            CU_TRY(cudaMemcpyAsync(ix->stage_in.p, static_cast<const char*>(x) + r0 * ix->d * esz,
-                                   static_cast<size_t>(m) * ix->d * esz, cudaMemcpyHostToDevice, st));
-            TRY(pack_dispatch(ix->stage_in.p, dtype, m, dst + r0 * ix->row_elems, ix, 0, nullptr, st));
-            CU_TRY(cudaStreamSynchronize(st));
-        }
+        TRY(ingest_host_rows(ix, static_cast<const char*>(x), n, dtype, esz, dst, st));
     }
     ix->ntotal += n;
     ix->has_groups = false;
@@ -735,6 +926,9 @@ int cvdb_index_set_groups(cvdb_index_t h, const int32_t* group_db, int on_device
         ix->has_groups = false;
         return CVDB_OK;
     }
+    if (ix->permuted())
+        return fail(CVDB_EINVAL, "group ids are indexed by stored position, and cvdb_index_group_by_list re-stored the rows "
+                                 "list-major: exclusion is not available on such an index (cvdb_index_reset clears)");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TRY(ix->groups.ensure(static_cast<size_t>(std::max<int64_t>(ix->ntotal, 1)) * 4));
@@ -757,10 +951,12 @@ int cvdb_index_search(cvdb_index_t h, const void* q, int64_t nq, int dtype, int 
     if (!q || !D || !I) return fail(CVDB_EINVAL, "q, D and I must be non-null");
     if (opts && opts->group_q && !ix->has_groups)
         return fail(CVDB_EINVAL, "group_q given but the index has no groups (cvdb_index_set_groups)");
-    if (ix->grouped)
-        return fail(CVDB_EINVAL, "rows are stored list-major (cvdb_index_group_by_list): use cvdb_index_search_lists");
+    if (ix->permuted() && opts && (opts->self_ids || opts->group_q))
+        return fail(CVDB_EINVAL, "self / group exclusion works on stored positions, and cvdb_index_group_by_list re-stored "
+                                 "the rows list-major: not available on such an index");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
     const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     const int64_t chunk = query_chunk(ix, k);
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -810,6 +1006,7 @@ int cvdb_index_assign(cvdb_index_t h, const void* x, int64_t n, int dtype, int32
     if (!x || !assign) return fail(CVDB_EINVAL, "x and assign must be non-null");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
     const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     const int64_t chunk = query_chunk(ix, 1);
     for (int64_t q0 = 0; q0 < n; q0 += chunk) {
@@ -887,6 +1084,7 @@ int cvdb_index_group_by_list(cvdb_index_t h, const int32_t* list_of_id, int nlis
     if (ix->ntotal == 0) return fail(CVDB_EINVAL, "empty index");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
     const int64_t n = ix->ntotal;
     const int row_vec16 = ix->row_elems * 2 / 16;
     // ids of the rows as stored now: what an earlier grouping left, then insertion order for rows added since
@@ -966,6 +1164,7 @@ int cvdb_index_search_lists(cvdb_index_t h, const void* q, int64_t nq, int dtype
     if (!q || !probes || !D || !I) return fail(CVDB_EINVAL, "q, probes, D and I must be non-null");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
     const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;  // bf16 and fp16 are 2 bytes
     // bound the gathered-query scratch: at most 2^18 (query, probe) pairs per launch
     const int64_t chunk = std::max<int64_t>(1, (int64_t(1) << 18) / nprobe);
@@ -1003,6 +1202,7 @@ int cvdb_build_triplets(const int64_t* I, const float* D, int64_t n, int k, cons
     if (metric != CVDB_METRIC_IP && metric != CVDB_METRIC_L2) return fail(CVDB_EINVAL, "unknown metric %d", metric);
     if (n == 0) return CVDB_OK;
     if (!I || !D || !pos || !out) return fail(CVDB_EINVAL, "null pointer");
+    ptr_guard g(I);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     build_triplets_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(I, D, n, k, pos, anchor_base, skip_top,
                                                                                     per_anchor, metric == CVDB_METRIC_L2,
@@ -1020,6 +1220,9 @@ int cvdb_index_export_rows(cvdb_index_t h, int64_t row0, int64_t nrows, void* ho
     if (row0 < 0 || nrows < 0 || row0 + nrows > ix->ntotal) return fail(CVDB_EINVAL, "row range outside the index");
     if (nrows == 0) return CVDB_OK;
     if (!host_dst) return fail(CVDB_EINVAL, "null pointer");
+    if (ix->permuted())
+        return fail(CVDB_EINVAL, "rows are stored list-major (cvdb_index_group_by_list); the dump format has no row ids: "
+                                 "export the index before grouping it");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t rb = static_cast<size_t>(ix->row_elems) * 2;
@@ -1063,32 +1266,89 @@ int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, 
     const size_t n_in = static_cast<size_t>(nq) * nlists * k_in, n_out = static_cast<size_t>(nq) * k;
     const unsigned blocks = static_cast<unsigned>(ceil_div(nq, 8));
     if (on_device) {
+        ptr_guard g(Dc);
         merge_lists_kernel<<<blocks, 256, 0, st>>>(Dc, Ic, nq, nlists, k_in, k, metric == CVDB_METRIC_L2, D, I);
         ++g_launches;
         CU_TRY(cudaGetLastError());
         return CVDB_OK;
     }
-    void *dDc = nullptr, *dIc = nullptr, *dD = nullptr, *dI = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(dDc); cudaFree(dIc); cudaFree(dD); cudaFree(dI);
-    };
-    cudaError_t e;
-    if ((e = cudaMalloc(&dDc, n_in * 4)) != cudaSuccess || (e = cudaMalloc(&dIc, n_in * 8)) != cudaSuccess ||
-        (e = cudaMalloc(&dD, n_out * 4)) != cudaSuccess || (e = cudaMalloc(&dI, n_out * 8)) != cudaSuccess) {
-        cleanup();
-        return fail(CVDB_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    // host pointers: one stream-ordered scratch allocation (pooled by the driver, no cudaMalloc per call),
+    // laid out [Dc | D | Ic | I] so the 8-byte arrays stay aligned; every copy is checked
+    const size_t off_d = (n_in * 4 + 255) & ~size_t(255);
+    const size_t off_ic = (off_d + n_out * 4 + 255) & ~size_t(255);
+    const size_t off_i = off_ic + n_in * 8;
+    char* scratch = nullptr;
+    CU_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), off_i + n_out * 8, st));
+    cudaError_t e = cudaMemcpyAsync(scratch, Dc, n_in * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + off_ic, Ic, n_in * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        merge_lists_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch),
+                                                   reinterpret_cast<const int64_t*>(scratch + off_ic), nq, nlists, k_in, k,
+                                                   metric == CVDB_METRIC_L2, reinterpret_cast<float*>(scratch + off_d),
+                                                   reinterpret_cast<int64_t*>(scratch + off_i));
+        ++g_launches;
+        e = cudaGetLastError();
     }
-    cudaMemcpyAsync(dDc, Dc, n_in * 4, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dIc, Ic, n_in * 8, cudaMemcpyHostToDevice, st);
-    merge_lists_kernel<<<blocks, 256, 0, st>>>(static_cast<float*>(dDc), static_cast<int64_t*>(dIc), nq, nlists, k_in, k,
-                                               metric == CVDB_METRIC_L2, static_cast<float*>(dD), static_cast<int64_t*>(dI));
-    ++g_launches;
-    cudaMemcpyAsync(D, dD, n_out * 4, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(I, dI, n_out * 8, cudaMemcpyDeviceToHost, st);
-    e = cudaStreamSynchronize(st);
-    cleanup();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(D, scratch + off_d, n_out * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(I, scratch + off_i, n_out * 8, cudaMemcpyDeviceToHost, st);
+    const cudaError_t ef = cudaFreeAsync(scratch, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = ef != cudaSuccess ? ef : es;
     if (e != cudaSuccess) return fail(CVDB_ECUDA, "merge failed: %s", cudaGetErrorString(e));
     return CVDB_OK;
+}
+
+// ------------------------------------------------------------ shard exchange in keys
+int cvdb_index_search_keys(cvdb_index_t h, const void* q, int64_t nq, int dtype, int k, uint64_t* keys,
+                           const cvdb_search_opts* opts, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (nq < 0) return fail(CVDB_EINVAL, "nq < 0");
+    if (k < 1 || k > CVDB_MAX_K) return fail(CVDB_ELIMIT, "k=%d outside [1, %d]", k, CVDB_MAX_K);
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (nq == 0) return CVDB_OK;
+    if (!q || !keys) return fail(CVDB_EINVAL, "q and keys must be non-null");
+    if (opts && opts->group_q && !ix->has_groups)
+        return fail(CVDB_EINVAL, "group_q given but the index has no groups (cvdb_index_set_groups)");
+    if (ix->permuted() && opts && (opts->self_ids || opts->group_q))
+        return fail(CVDB_EINVAL, "self / group exclusion is not available on an index re-stored list-major");
+    const int64_t id_base = opts ? opts->id_base : 0;
+    if (id_base < 0 || id_base + ix->ntotal > 0xFFFFFFFELL)
+        return fail(CVDB_ELIMIT, "keys carry 32-bit ids: id_base + ntotal must stay below 2^32 - 1");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    const size_t esz = dtype == CVDB_DTYPE_F32 ? 4 : 2;
+    TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));  // kept for cvdb_index_merge_keys (L2 needs |q|^2)
+    const int64_t chunk = query_chunk(ix, k);
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t m = std::min(chunk, nq - q0);
+        const void* qsrc = static_cast<const char*>(q) + q0 * ix->d * esz;
+        const int32_t* self = (opts && opts->self_ids) ? opts->self_ids + q0 : nullptr;
+        const int32_t* grp = (opts && opts->group_q) ? opts->group_q + q0 : nullptr;
+        TRY(search_device(ix, qsrc, m, dtype, k, nullptr, nullptr, nullptr, self, grp, opts, st, keys + q0 * k,
+                          ix->q_norm.as<float>() + q0));
+    }
+    return CVDB_OK;
+}
+
+int cvdb_index_merge_keys(cvdb_index_t h, const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, float* D,
+                          int64_t* I, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (nq < 0 || nlists < 1 || k_in < 1 || k < 1 || k > CVDB_MAX_K) return fail(CVDB_EINVAL, "bad sizes");
+    if (nq == 0) return CVDB_OK;
+    if (!keys || !D || !I) return fail(CVDB_EINVAL, "null pointer");
+    const int l2 = ix->metric == CVDB_METRIC_L2;
+    if (l2 && ix->q_norm.cap < static_cast<size_t>(nq) * 4)
+        return fail(CVDB_EINVAL, "L2 distances need the query norms of the preceding cvdb_index_search_keys call "
+                                 "(same queries, same handle)");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    return launch_merge(keys, nq, nlists, k_in, k, l2, ix->q_norm.as<float>(), 0, k_in, static_cast<int64_t>(nq) * k_in,
+                        nullptr, 0, D, I, nullptr, nullptr, st);
 }
 
 int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int32_t* assign, float* sums,
@@ -1096,6 +1356,7 @@ int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int
     if (n < 0 || d < 1) return fail(CVDB_EINVAL, "bad sizes");
     if (n == 0) return CVDB_OK;
     if (!x || !assign || !sums || !counts) return fail(CVDB_EINVAL, "null pointer");
+    ptr_guard g(sums);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t blocks = std::min<int64_t>(ceil_div(n, 8), 148 * 16);
     if (dtype == CVDB_DTYPE_F32)
@@ -1117,6 +1378,7 @@ int cvdb_kmeans_accumulate(const void* x, int64_t n, int d, int dtype, const int
 int cvdb_kmeans_finalize(const float* sums, const int32_t* counts, int K, int d, float* centroids, void* stream) {
     if (K < 1 || d < 1) return fail(CVDB_EINVAL, "bad sizes");
     if (!sums || !counts || !centroids) return fail(CVDB_EINVAL, "null pointer");
+    ptr_guard g(centroids);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t total = static_cast<int64_t>(K) * d;
     kmeans_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, st>>>(sums, counts, K, d, centroids);
@@ -1129,6 +1391,7 @@ int cvdb_kmeans_split_empty(float* centroids, int32_t* counts, int K, int d, flo
     if (K < 1 || d < 1) return fail(CVDB_EINVAL, "bad sizes");
     if (!centroids || !counts) return fail(CVDB_EINVAL, "null pointer");
     if (!(eps >= 0.f && eps < 1.f)) return fail(CVDB_EINVAL, "eps must be in [0, 1)");
+    ptr_guard g(centroids);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     kmeans_split_empty_kernel<<<1, 1024, 0, st>>>(centroids, counts, K, d, eps, n_split);
     ++g_launches;

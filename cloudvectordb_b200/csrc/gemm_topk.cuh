@@ -89,7 +89,10 @@ struct LaneTopk<0> {
 // least k rows score >= it, so any row scoring strictly less can be dropped by
 // every other slice too.  Equal scores must still pass (the tie rule is decided
 // by row id at the merge), hence the "- 1" when adopting a foreign threshold.
+// The next code below +0.0 (0x80000000) would be -0.0, and `s > -0.0f` is false for s == +0.0: step to a
+// negative number instead (any value below the shared score is a valid filter bound; keys decide ties).
 __device__ __forceinline__ float thr_from_shared(uint32_t g) {
+    if (g == 0x80000000u) return -1.17549435e-38f;
     return g > 1u ? ordered_to_float(g - 1u) : -INFINITY;
 }
 // strict_own: rows still to come in this item have larger ids than everything collected so far (true for the

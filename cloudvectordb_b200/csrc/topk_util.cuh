@@ -15,6 +15,7 @@ __host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
 #else
     union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
 #endif
+    if (u == 0x80000000u) u = 0;  // -0.0 == +0.0: one code for both, or equal scores would order by sign
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {

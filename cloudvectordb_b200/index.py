@@ -213,6 +213,39 @@ class IndexFlat:
             return torch.from_numpy(Dn), torch.from_numpy(In)
         return Dn, In
 
+    # -- shard exchange in the engine's own candidate keys (include/cvdb_b200.h: cvdb_index_search_keys) ------
+    def search_keys(self, q, k: int, *, self_ids=None, group_q=None, id_base: int = 0, profile: bool = False):
+        """search() whose result stays in the kernel's 64-bit keys: int64 tensor [nq, k] on the GPU (the bit
+        pattern of (ordered score << 32 | ~id), sorted best first, 0 = no result).  Ids include ``id_base``.
+        This is what the ranks of a ShardedIndex exchange: one 8-byte word per candidate."""
+        b = _Buf(q, self._d, "q")
+        if not b.on_device:
+            raise ValueError("search_keys() takes CUDA tensors (the exchange runs on the device)")
+        self._check_place(b)
+        k = int(k)
+        opts = _C.SearchOpts()
+        sp, keep_s = _i32_buf(self_ids, b.n, b, "self_ids")
+        gp, keep_g = _i32_buf(group_q, b.n, b, "group_q")
+        opts.self_ids, opts.group_q, opts.id_base, opts.profile = sp, gp, int(id_base), int(profile)
+        keys = torch.empty((b.n, k), dtype=torch.int64, device=f"cuda:{b.device_index}")
+        _C.check(_C.lib().cvdb_index_search_keys(self._h, b.ptr, b.n, b.dtype, k, keys.data_ptr(), C.byref(opts),
+                                                 _stream_for(b)))
+        del keep_s, keep_g
+        return keys
+
+    def merge_keys(self, keys, k: int):
+        """k-way merge of key lists [nlists, nq, k_in] (an all_gather_into_tensor of every rank's search_keys
+        result for the SAME queries) -> (D [nq, k] f32, I [nq, k] i64) on the GPU."""
+        if not (_is_torch(keys) and keys.is_cuda and keys.dtype == torch.int64 and keys.dim() == 3):
+            raise ValueError("keys must be a CUDA int64 tensor [nlists, nq, k_in]")
+        keys = keys.contiguous()
+        nl, nq, k_in = (int(v) for v in keys.shape)
+        D = torch.empty((nq, int(k)), dtype=torch.float32, device=keys.device)
+        I = torch.empty((nq, int(k)), dtype=torch.int64, device=keys.device)
+        _C.check(_C.lib().cvdb_index_merge_keys(self._h, keys.data_ptr(), nq, nl, k_in, int(k), D.data_ptr(), I.data_ptr(),
+                                                int(torch.cuda.current_stream(keys.device.index).cuda_stream)))
+        return D, I
+
     def assign(self, x, return_dist: bool = True):
         """Nearest index row of every x (k = 1): (assign int32 [n], dist f32 [n])."""
         b = _Buf(x, self._d, "x")
@@ -271,7 +304,7 @@ class IndexFlat:
                 _C.check(_C.lib().cvdb_index_import_rows(idx._h, buf.ctypes.data, m, None))
         return idx
 
-    def add_from_file(self, path: str, dtype: str = "float32", chunk_rows: int = 1 << 18, offset: int = 0) -> int:
+    def add_from_file(self, path: str, dtype: str = "float32", chunk_rows: int = 1 << 20, offset: int = 0) -> int:
         """Streaming add() of a raw row-major [n, d] matrix on disk (float32 or bfloat16), memory-mapped
         and fed in chunks so the corpus never has to be resident on the host.  Returns the rows added."""
         esz = {"float32": 4, "bfloat16": 2, "float16": 2}[dtype]
@@ -280,9 +313,12 @@ class IndexFlat:
             raise ValueError("file size is not a whole number of rows")
         n = size // (esz * self._d)
         mm = np.memmap(path, dtype=np.float32 if esz == 4 else np.uint16, mode="r", offset=offset, shape=(n, self._d))
+        code = {"float32": _C.DTYPE_F32, "bfloat16": _C.DTYPE_BF16, "float16": _C.DTYPE_F16}[dtype]
+        self.reserve(self.ntotal + int(n))
         for r0 in range(0, n, chunk_rows):
-            blk = np.ascontiguousarray(mm[r0:r0 + chunk_rows])
-            code = {"float32": _C.DTYPE_F32, "bfloat16": _C.DTYPE_BF16, "float16": _C.DTYPE_F16}[dtype]
+            # a row range of the mapping is contiguous already: the library reads it in place (its host threads
+            # copy 64 MB pieces into pinned staging buffers while the previous piece is on the PCIe bus)
+            blk = mm[r0:r0 + chunk_rows]
             _C.check(_C.lib().cvdb_index_add(self._h, blk.ctypes.data, blk.shape[0], code, 0, None))
         return int(n)
 

@@ -96,13 +96,22 @@ class IndexIVFFlat:
         return I.to(torch.int32).contiguous()
 
     def search(self, q, k: int, nprobe: Optional[int] = None):
-        if self.ntotal == 0:
-            raise RuntimeError("empty index")
-        if not self._grouped:
-            self._group()
         host_out = not (isinstance(q, torch.Tensor) and q.is_cuda)
         as_numpy = isinstance(q, np.ndarray)
         qd = self._to_device(q)
+        if self.ntotal == 0:
+            # nothing to scan (an empty shard of a sharded index must still reach the collective): all padding
+            nq = int(qd.shape[0]) if qd.dim() == 2 else 1
+            D = torch.full((nq, k), float("inf") if self.metric == "l2" else float("-inf"), dtype=torch.float32,
+                           device=self._dev())
+            I = torch.full((nq, k), -1, dtype=torch.int64, device=self._dev())
+            if host_out:
+                D, I = D.cpu(), I.cpu()
+                if as_numpy:
+                    return D.numpy(), I.numpy()
+            return D, I
+        if not self._grouped:
+            self._group()
         probes = self.probe(qd, nprobe)
         b = _Buf(qd, self.d, "q")
         D = torch.empty((b.n, k), dtype=torch.float32, device=self._dev())

@@ -45,7 +45,15 @@ class Kmeans:
         return x.to(self._dev()).contiguous()
 
     def init_centroids(self, x: torch.Tensor) -> torch.Tensor:
-        """k distinct local points chosen with `seed` (rank 0's choice is broadcast)."""
+        """k distinct local points chosen with `seed` (rank 0's choice is broadcast).  Every rank checks the
+        SAME condition (rank 0's point count, shared by a collective), so either all raise or none does."""
+        n0 = torch.tensor([int(x.shape[0])], dtype=torch.int64, device=x.device)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.broadcast(n0, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                           group=self.group)
+        if int(n0.item()) < self.k:
+            raise ValueError(f"k-means with k={self.k} needs at least k points on the initialising rank "
+                             f"(it holds {int(n0.item())}); pass init_centroids= or fewer clusters")
         g = torch.Generator(device="cpu").manual_seed(self.seed)
         perm = torch.randperm(x.shape[0], generator=g)[: self.k].to(x.device)
         c = x[perm].float().contiguous()

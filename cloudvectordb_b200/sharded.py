@@ -1,7 +1,8 @@
 """Shard/merge layer: the database is row-sharded over the ranks of a
 ``torch.distributed`` group (one process per GPU); every rank searches its
-shard with the fused kernel, the per-rank (D, I) candidates are exchanged with
-ONE all-gather (NCCL over NVLink) and each rank does the final k-way select.
+shard with the fused kernel, the per-rank candidates are exchanged with ONE
+all-gather (NCCL over NVLink; [nq, k] 64-bit keys per rank) and each rank does
+the final k-way select (a head-pointer merge of the sorted per-rank lists).
 
 Top-k over a union of row sets == top-k of the per-set top-k lists, so this is
 the only collective on the path.  Global ids are the
@@ -26,9 +27,9 @@ def shard_bounds(n: int, world: int, rank: int):
 
 class ShardedIndex:
     def __init__(self, d: int, metric: str = "ip", storage: str = "bf16", device: Optional[int] = None,
-                 group=None, local_index=None, merge_fn: Optional[Callable] = None):
-        """`local_index` / `merge_fn` exist so the host logic can be exercised on CPU
-        (gloo) with stand-ins; the product path builds an IndexFlat on `device`."""
+                 group=None, local_index=None):
+        """`local_index` exists so the host logic can be exercised on CPU (gloo) with a stand-in that offers
+        the same search / search_keys / merge_keys surface; the product path builds an IndexFlat on `device`."""
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -40,7 +41,6 @@ class ShardedIndex:
             local_index = IndexFlat(d, metric, storage, device)
         self.device = device
         self.local = local_index
-        self.merge_fn = merge_fn or merge_topk
         self.id_base = 0
         self._ntotal = 0
         self._counts = [0] * self.world
@@ -93,17 +93,15 @@ class ShardedIndex:
             s = torch.as_tensor(self_ids).to(torch.int64)
             in_shard = (s >= self.id_base) & (s < self.id_base + self._counts[self.rank])
             local_self = torch.where(in_shard, s - self.id_base, torch.full_like(s, -1)).to(torch.int32)
-        D, I = self.local.search(q, k, self_ids=local_self, group_q=group_q, id_base=self.id_base, **kw)
         if self.world == 1:
-            return D, I
-        D = torch.as_tensor(D)
-        I = torch.as_tensor(I)
-        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-        # one exchange step: every rank receives every rank's k candidates per query
-        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
-        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
-        Dm, Im = self.merge_fn(Dg, Ig, k, self.metric)
+            return self.local.search(q, k, self_ids=local_self, group_q=group_q, id_base=self.id_base, **kw)
+        # one exchange step, in the kernel's own 64-bit candidate keys: every rank contributes its sorted top-k
+        # (8 bytes per candidate, ids already global) to ONE all_gather_into_tensor, then merges the `world`
+        # sorted lists per query with a head-pointer merge
+        keys = self.local.search_keys(q, k, self_ids=local_self, group_q=group_q, id_base=self.id_base, **kw)
+        gathered = torch.empty((self.world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        dist.all_gather_into_tensor(gathered.view(-1, keys.shape[-1]), keys.contiguous(), group=self.group)
+        Dm, Im = self.local.merge_keys(gathered, k)
         if host_io:
             return Dm.cpu(), Im.cpu()
         return Dm, Im
@@ -158,8 +156,8 @@ class ShardedIVFFlat:
             return D, I
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
-        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(Dg.view(-1, D.shape[-1]), D.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(Ig.view(-1, I.shape[-1]), I.contiguous(), group=self.group)
         return merge_topk(Dg, Ig, k, self.metric)
 
     def close(self) -> None:

@@ -23,7 +23,11 @@
  *   - search results: IP sorted by descending score, L2 by ascending SQUARED
  *     distance, ties broken by lower id; missing results have I = -1 and
  *     D = -inf (IP) / +inf (L2).
- *   - one index handle is not thread-safe; distinct handles are.
+ *   - one index handle is not thread-safe; distinct handles are.  Calls on one handle may use different
+ *     streams: a call first waits (on the device) for the previous call's work when its stream differs,
+ *     because the handle's scratch buffers are shared between calls.
+ *   - functions without a handle take device pointers and run on the device that owns them, whatever the
+ *     caller's current device is.
  *   - there is no CPU fallback: without a B200-class GPU every compute entry
  *     point fails with CVDB_ECUDA.
  */
@@ -81,11 +85,14 @@ int cvdb_index_create(int d, int metric, int storage, int device, cvdb_index_t* 
 int cvdb_index_destroy(cvdb_index_t idx);
 int cvdb_index_reset(cvdb_index_t idx);               /* ntotal = 0, keeps the allocation   */
 int cvdb_index_reserve(cvdb_index_t idx, int64_t n);  /* capacity for n rows in total       */
-int cvdb_index_truncate(cvdb_index_t idx, int64_t n); /* drop the rows added last: ntotal = n <= ntotal (flat layout only) */
+int cvdb_index_truncate(cvdb_index_t idx, int64_t n); /* drop the rows added last: ntotal = n <= ntotal; after
+                                                         cvdb_index_group_by_list only rows added since can go */
 int64_t cvdb_index_ntotal(cvdb_index_t idx);
 int cvdb_index_dim(cvdb_index_t idx);
 
-/* FAISS add(x): append n rows (copied; caller keeps ownership of x). */
+/* FAISS add(x): append n rows (copied; caller keeps ownership of x).  Host rows stream through two pinned
+ * 64 MB staging buffers (host copy, PCIe copy and the packing kernel of consecutive chunks overlap); memory the
+ * caller pinned itself is read in place.  Returns once x may be reused. */
 int cvdb_index_add(cvdb_index_t idx, const void* x, int64_t n, int dtype, int on_device, void* stream);
 
 /* Input validation without a hidden synchronisation on the hot path (SURVEY.md 4.2 "NaN/Inf rejection"): the
@@ -124,7 +131,11 @@ int cvdb_index_last_variant(cvdb_index_t idx);
  * cvdb_index_group_by_list re-stores the rows list-major.  list_of_id [ntotal] (int32, DEVICE pointer) names the
  * list (0..nlist-1) of every row, indexed by row id (= insertion order).  Rows added after an earlier grouping are
  * picked up by calling it again with the complete vector.  bf16 storage only.  The order of rows inside a list is
- * unspecified; results do not depend on it (candidates carry their row id).  add() un-groups the index.
+ * unspecified; results do not depend on it (candidates carry their row id).  add() un-groups the index: list
+ * search is refused until it is grouped again, while cvdb_index_search / cvdb_index_assign keep working on the
+ * re-stored rows and keep returning the ids the rows were added under.  What addresses rows by stored position
+ * -- cvdb_index_set_groups, self / group exclusion, cvdb_index_export_rows, truncating below the grouped rows --
+ * fails with CVDB_EINVAL from the first grouping until cvdb_index_reset.
  * cvdb_index_list_offsets copies the nlist+1 list boundaries (stored positions) to a DEVICE buffer.
  * cvdb_index_search_lists: like cvdb_index_search, but query i only scans the lists probes[i][0..nprobe)
  * (int32, follows on_device; entries < 0 are skipped).  Returned ids are row ids. */
@@ -153,6 +164,18 @@ int cvdb_index_import_rows(cvdb_index_t idx, const void* host_src, int64_t nrows
  * (what an all-gather of per-rank (D, I) produces).  Output [nq][k]. */
 int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, int k_in, int k, int metric,
                     float* D, int64_t* I, int on_device, void* stream);
+
+/* The same exchange in the engine's own 64-bit candidate keys (8 bytes per candidate instead of 12, one buffer
+ * instead of two, and the final merge is a head-pointer merge of sorted lists):
+ *   cvdb_index_search_keys: like cvdb_index_search with DEVICE pointers, but writes keys [nq][k] (uint64, sorted
+ *     descending, 0 = no result) whose id field already includes opts->id_base (must stay below 2^32 - 1);
+ *   cvdb_index_merge_keys: k-way merge of `nlists` such lists laid out [nlists][nq][k_in] (an
+ *     all_gather_into_tensor of every rank's keys) -> D [nq][k] f32, I [nq][k] i64, DEVICE pointers.  For L2 it uses
+ *     the query norms the preceding cvdb_index_search_keys call on this handle computed (same queries). */
+int cvdb_index_search_keys(cvdb_index_t idx, const void* q, int64_t nq, int dtype, int k, uint64_t* keys,
+                           const cvdb_search_opts* opts, void* stream);
+int cvdb_index_merge_keys(cvdb_index_t idx, const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, float* D,
+                          int64_t* I, void* stream);
 
 /* -- k-means update (IVF coarse quantizer) --------------------------------
  * sums [K,d] f32 += x[i] for assign[i]; counts [K] i32 += 1.  The caller zeroes

@@ -138,10 +138,30 @@ class OracleLocalIndex:
         I = np.where(I >= 0, I + id_base, -1)
         return torch.from_numpy(D), torch.from_numpy(I)
 
+    # the exchange format of the product path, restated in NumPy: key = ordered(score) << 32 | ~id, where the score
+    # is "larger is better" (IP: the score, L2: minus the squared distance); 0 = no result
+    def search_keys(self, q, k, self_ids=None, group_q=None, id_base=0):
+        D, I = self.search(q, k, self_ids=self_ids, group_q=group_q, id_base=id_base)
+        D, I = D.numpy(), I.numpy()
+        s = (D if self.metric == "ip" else -D).astype(np.float32)
+        u = np.where(I >= 0, s, np.float32(0)).view(np.uint32).astype(np.uint64)
+        u = np.where(u == 0x80000000, 0, u)                                       # -0.0 == +0.0
+        o = np.where(u & 0x80000000, ~u & 0xFFFFFFFF, u | 0x80000000)
+        key = (o << np.uint64(32)) | (~I.astype(np.uint64) & np.uint64(0xFFFFFFFF))
+        key = np.where(I >= 0, key, np.uint64(0))
+        return torch.from_numpy(key.view(np.int64).copy())
 
-def oracle_merge(Dg, Ig, k, metric):
-    Dm, Im = O.merge_ref(list(Dg.numpy()), list(Ig.numpy()), k, O.METRIC_IP if metric == "ip" else O.METRIC_L2)
-    return torch.from_numpy(Dm), torch.from_numpy(Im)
+    def merge_keys(self, keys, k):
+        key = keys.numpy().view(np.uint64)                                         # [lists, nq, k_in]
+        nl, nq, k_in = key.shape
+        flat = np.transpose(key, (1, 0, 2)).reshape(nq, nl * k_in)
+        top = np.sort(flat, axis=1)[:, ::-1][:, :k]                                # uint64 keys: larger is better
+        o = (top >> np.uint64(32)).astype(np.uint32)
+        u = np.where(o & 0x80000000, o & 0x7FFFFFFF, ~o).astype(np.uint32)
+        s = u.view(np.float32)
+        I = np.where(top != 0, (~top & np.uint64(0xFFFFFFFF)).astype(np.int64), -1)
+        D = np.where(top != 0, s if self.metric == "ip" else -s, -np.inf if self.metric == "ip" else np.inf)
+        return torch.from_numpy(D.astype(np.float32)), torch.from_numpy(I)
 
 
 def _free_port():
@@ -163,7 +183,7 @@ def _worker(rank, world, port, metric, q):
         xq = rng.standard_normal((nq, d), dtype=np.float32)
         groups = (np.arange(n) // 4).astype(np.int32)
         self_ids = rng.integers(0, n, nq)
-        idx = ShardedIndex(d, metric, local_index=OracleLocalIndex(d, metric), merge_fn=oracle_merge)
+        idx = ShardedIndex(d, metric, local_index=OracleLocalIndex(d, metric))
         idx.add(xb)
         lo, hi = shard_bounds(n, world, rank)
         assert idx.local.ntotal == hi - lo and idx.id_base == lo and idx.ntotal == n
@@ -213,7 +233,7 @@ def _mining_worker(rank, world, port, q):
         emb = rng.standard_normal((n, d), dtype=np.float32)
         groups = (np.arange(n) // 3).astype(np.int32)
         lo, hi = (0, 300) if rank == 0 else (300, n)               # uneven shards, ragged last chunk
-        idx = ShardedIndex(d, "ip", local_index=OracleLocalIndex(d, "ip"), merge_fn=oracle_merge)
+        idx = ShardedIndex(d, "ip", local_index=OracleLocalIndex(d, "ip"))
         idx.add_local(emb[lo:hi])
         assert idx.ntotal == n and idx.id_base == lo
         idx.set_groups_local(groups[lo:hi])
