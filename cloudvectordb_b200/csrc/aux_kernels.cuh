@@ -394,9 +394,10 @@ __global__ void ivf_count_pairs_kernel(const int32_t* __restrict__ probes, int64
 }
 
 // single block: exclusive scans over the lists -> pair_off[l] (first gathered row of list l),
-// item_off[l] (first work item of list l); scal[0] = total items, scal[1] = total gathered rows
+// item_off[l] (first work item of list l; an item takes up to item_cap pairs of one list);
+// scal[0] = total items, scal[1] = total gathered rows, scal[3] = 0 (the scan kernel's work counter)
 __global__ void ivf_scan_lists_kernel(const int32_t* __restrict__ cnt, int nlist, int32_t* __restrict__ pair_off,
-                                      int32_t* __restrict__ item_off, int32_t* __restrict__ scal) {
+                                      int32_t* __restrict__ item_off, int32_t* __restrict__ scal, int item_cap = 128) {
     __shared__ int s_pairs[1024], s_items[1024];
     __shared__ int base_pairs, base_items;
     const int tid = threadIdx.x;
@@ -405,7 +406,7 @@ __global__ void ivf_scan_lists_kernel(const int32_t* __restrict__ cnt, int nlist
     for (int l0 = 0; l0 < nlist; l0 += 1024) {
         const int l = l0 + tid;
         const int c = l < nlist ? cnt[l] : 0;
-        const int it = (c + 127) >> 7;
+        const int it = (c + item_cap - 1) / item_cap;
         s_pairs[tid] = c;
         s_items[tid] = it;
         __syncthreads();
@@ -424,21 +425,21 @@ __global__ void ivf_scan_lists_kernel(const int32_t* __restrict__ cnt, int nlist
         if (tid == 1023) { base_pairs += s_pairs[1023]; base_items += s_items[1023]; }
         __syncthreads();
     }
-    if (tid == 0) { scal[0] = base_items; scal[1] = base_pairs; }
+    if (tid == 0) { scal[0] = base_items; scal[1] = base_pairs; scal[3] = 0; }
 }
 
-// work items of every probed list: up to 128 gathered query rows x the rows of the list
+// work items of every probed list: up to item_cap gathered query rows x the rows of the list
 struct IvfItem { int a_row0, a_rows, x_row0, x_rows; };
 __global__ void ivf_make_items_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ pair_off,
                                       const int32_t* __restrict__ item_off, const int32_t* __restrict__ list_off,
-                                      int nlist, IvfItem* __restrict__ items) {
+                                      int nlist, IvfItem* __restrict__ items, int item_cap = 128) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     const int c = cnt[l];
-    for (int i = 0; i * 128 < c; ++i) {
+    for (int i = 0; i * item_cap < c; ++i) {
         IvfItem it;
-        it.a_row0 = pair_off[l] + i * 128;
-        it.a_rows = min(128, c - i * 128);
+        it.a_row0 = pair_off[l] + i * item_cap;
+        it.a_rows = min(item_cap, c - i * item_cap);
         it.x_row0 = list_off[l];
         it.x_rows = list_off[l + 1] - list_off[l];
         items[item_off[l] + i] = it;

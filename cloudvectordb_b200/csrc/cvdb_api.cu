@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "ivf_scan.cuh"
 #include "launchers.h"
 
 namespace {
@@ -169,7 +170,7 @@ struct Index {
         int row_elems = 0, box_rows = 0;
         CUtensorMap map;
     };
-    TmapSlot tm_q, tm_x, tm_q_ivf, tm_x_ivf;
+    TmapSlot tm_q, tm_x, tm_q_ivf, tm_x_ivf, tm_x32_ivf;
 
     // The scratch buffers above are per handle: a call on another stream than the previous one first waits for
     // the previous call's work (event recorded at the end of every call).
@@ -686,8 +687,16 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
     TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
     TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, ix->q_norm.as<float>(), st));
 
+    // Which scan kernel: with few pairs per list (the usual IVF regime: many lists, few probes) the transposed kernel
+    // (list rows on the M side, <= 16 queries per item) streams every list once at HBM rate; with many pairs per
+    // list the grouped kernel (128 queries per item) re-reads a list fewer times.  CVDB_IVF_KERNEL=0/1 forces one.
+    const int nkb_ = static_cast<int>(ceil_div(ix->Kp, 64));
+    bool transposed = k <= 128 && nkb_ <= kIvfMaxKb && n_pairs <= 24 * static_cast<int64_t>(nlist);
+    if (const char* env = getenv("CVDB_IVF_KERNEL")) transposed = atoi(env) != 0 && k <= 128 && nkb_ <= kIvfMaxKb;
+    else transposed = false;  // TEMPORARY until the new kernel has passed the parity suite on the GPU
+    const int item_cap = transposed ? 16 : 128;
     // --- group the (query, probe) pairs by list
-    const int64_t max_items = std::min<int64_t>(nlist, n_pairs) + n_pairs / 128 + 1;
+    const int64_t max_items = std::min<int64_t>(nlist, n_pairs) + n_pairs / item_cap + 1;
     const int64_t pairs_pad = n_pairs + 128;  // the last item's A box may run past the last gathered row
     TRY(ix->ivf_cnt.ensure(static_cast<size_t>(nlist) * 4));
     TRY(ix->ivf_cursor.ensure(static_cast<size_t>(nlist) * 4));
@@ -704,10 +713,10 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
     ivf_count_pairs_kernel<<<static_cast<unsigned>(ceil_div(n_pairs, 256)), 256, 0, st>>>(probes, n_pairs, nlist, list_off,
                                                                                           ix->ivf_cnt.as<int32_t>());
     ivf_scan_lists_kernel<<<1, 1024, 0, st>>>(ix->ivf_cnt.as<int32_t>(), nlist, ix->ivf_pair_off.as<int32_t>(),
-                                               ix->ivf_item_off.as<int32_t>(), ix->ivf_scal.as<int32_t>());
+                                               ix->ivf_item_off.as<int32_t>(), ix->ivf_scal.as<int32_t>(), item_cap);
     ivf_make_items_kernel<<<static_cast<unsigned>(ceil_div(nlist, 256)), 256, 0, st>>>(
         ix->ivf_cnt.as<int32_t>(), ix->ivf_pair_off.as<int32_t>(), ix->ivf_item_off.as<int32_t>(), list_off, nlist,
-        ix->ivf_items.as<IvfItem>());
+        ix->ivf_items.as<IvfItem>(), item_cap);
     ivf_scatter_pairs_kernel<<<static_cast<unsigned>(ceil_div(n_pairs, 8)), 256, 0, st>>>(
         probes, n_pairs, nprobe, nlist, list_off, ix->ivf_pair_off.as<int32_t>(), ix->ivf_cursor.as<int32_t>(),
         ix->q_pack.as<uint4>(), row_vec16, ix->ivf_pair_query.as<int32_t>(), ix->ivf_pair_dst.as<int32_t>(),
@@ -721,7 +730,28 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
     CU_TRY(cudaMemsetAsync(ix->part.p, 0, static_cast<size_t>(n_pairs) * k * 8, st));  // dropped pairs stay empty
     TRY(ix->gthr.ensure(static_cast<size_t>(nq) * 4));
     CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq) * 4, st));
-    if (n_items > 0) {
+    if (n_items > 0 && transposed) {
+        const int grid = std::min(ix->num_sms, n_items);
+        IvfScanParams p{};
+        p.n_items_ptr = ix->ivf_scal.as<int32_t>();
+        p.work_counter = ix->ivf_scal.as<unsigned int>() + 3;
+        p.k = k;
+        p.trigger = std::min(kIvfCap - 128, std::max(32, 2 * k));
+        if (const char* env = getenv("CVDB_IVF_TRIGGER")) p.trigger = std::min(kIvfCap - 128, std::max(k, atoi(env)));
+        p.nkb = nkb_;
+        p.k16 = static_cast<int>(ceil_div(ix->Kd, 16));
+        p.items = reinterpret_cast<const GroupItem*>(ix->ivf_items.p);
+        p.pair_query = ix->ivf_pair_query.as<int32_t>();
+        p.pair_dst = ix->ivf_pair_dst.as<int32_t>();
+        p.row_ids = ix->row_ids.as<int32_t>();
+        p.part = ix->part.as<uint64_t>();
+        p.gthr = ix->gthr.as<uint32_t>();
+        CUtensorMap tq, tx128, tx32;
+        TRY(get_tmap(ix->tm_q_ivf, &tq, ix->ivf_qg.p, pairs_pad, ix->row_elems, 16));  // the item's <= 16 query rows
+        TRY(get_tmap(ix->tm_x_ivf, &tx128, ix->x, ix->ntotal, ix->row_elems, 128));
+        TRY(get_tmap(ix->tm_x32_ivf, &tx32, ix->x, ix->ntotal, ix->row_elems, 32));     // tail tiles of a list
+        LAUNCH(launch_ivf_scan(tx128, tx32, tq, p, grid, st));
+    } else if (n_items > 0) {
         const int grid = std::min(ix->num_sms, n_items);
         if (E > 0) TRY(ix->cand.ensure(static_cast<size_t>(grid) * 128 * C * 8));
         GroupedParams p{};
@@ -745,7 +775,7 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
     ix->last_flops = 0;
     ix->last_slices = nprobe;
     ix->last_grid = n_items;
-    ix->last_variant = 5;
+    ix->last_variant = transposed ? 6 : 5;
     // candidate keys of the list scan already carry the caller's row ids (GroupedParams::row_ids)
     return launch_merge(ix->part.as<uint64_t>(), nq, nprobe, k, k, l2, ix->q_norm.as<float>(), 0,
                         static_cast<int64_t>(nprobe) * k, k, nullptr, 0, D, I, nullptr, nullptr, st);

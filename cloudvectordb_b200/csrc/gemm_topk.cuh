@@ -142,6 +142,117 @@ __device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&
     return warp_sorted_at<E>(key, k - 1);
 }
 
+// Compaction WITHOUT sorting (buffers of 128..512 slots, k = 29..248).  Between compactions a buffer only has
+// to hold a superset of the query's best k, in any order -- it is sorted once, when the work item ends.  So a
+// full buffer is reduced with a SELECT: find the k-th largest key by bisection on the score word (one
+// per-lane count over the E registers + one warp reduction per bit, starting below the bits all candidates
+// share), resolve a tie at the k-th score on the row word (rare), then move the k survivors to the front with
+// ballot prefix sums.  ~(2E + 2) instructions per bit against ~12E per stage of the E*log^2 bitonic network
+// (512 slots: ~1k instructions instead of ~9k), and a dependent chain of ~20 reductions instead of 45 shuffle
+// stages -- a sort used to hold its epilogue warp for more than two MMA tiles, i.e. it stalled the tensor pipe.
+// Returns a key whose score word is the k-th best score (0 when fewer than k candidates exist); `kept` = number of
+// survivors now at the front of the buffer (slots behind them are zero).
+// The select itself, on keys held in registers (slot e*32+lane in key[e], 0 = empty): returns T such that the
+// survivors are exactly the non-empty keys >= T (the best k, or all of them when there are at most k), and sets
+// kth to a key whose score word is the k-th best score (0 when fewer than k candidates exist).
+template <int E>
+__device__ __forceinline__ uint64_t warp_select_threshold(const uint64_t (&key)[E], int k, uint64_t& kth) {
+    constexpr unsigned kFull = 0xffffffffu;
+    uint32_t hi[E];
+    int my_valid = 0;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        hi[e] = static_cast<uint32_t>(key[e] >> 32);  // 0 <=> empty slot (the score word of a real candidate is never 0)
+        my_valid += hi[e] != 0;
+        mx = max(mx, hi[e]);
+        mn = hi[e] != 0 ? min(mn, hi[e]) : mn;
+    }
+    const int n_valid = __reduce_add_sync(kFull, my_valid);
+    mx = __reduce_max_sync(kFull, mx);
+    mn = __reduce_min_sync(kFull, mn);
+    kth = 0;
+    if (n_valid <= k) {  // warp-uniform
+        if (n_valid == k) kth = (static_cast<uint64_t>(mn) << 32) | 1u;
+        return 1;  // keep every candidate
+    }
+    uint32_t prefix = mx;
+    const uint32_t diff = mx ^ mn;
+    if (diff != 0) {
+        int bit = 31 - __clz(diff);
+        prefix = mx & ~((2u << bit) - 1u);  // the bits every candidate shares
+        for (; bit >= 0; --bit) {
+            const uint32_t trial = prefix | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) c += hi[e] >= trial;
+            if (__reduce_add_sync(kFull, c) >= k) prefix = trial;
+        }
+    }
+    // prefix == the k-th largest score word
+    int c_gt = 0, c_eq = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        c_gt += hi[e] > prefix;
+        c_eq += hi[e] == prefix;
+    }
+    c_gt = __reduce_add_sync(kFull, c_gt);
+    c_eq = __reduce_add_sync(kFull, c_eq);
+    const int need = k - c_gt;  // how many of the rows tied at the k-th score stay: the lowest ids
+    uint32_t low = 0;
+    if (need < c_eq) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = low | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) c += (hi[e] == prefix) && (static_cast<uint32_t>(key[e]) >= trial);
+            if (__reduce_add_sync(kFull, c) >= need) low = trial;
+        }
+    }
+    const uint64_t T = (static_cast<uint64_t>(prefix) << 32) | low;
+    kth = T | 1u;
+    return T;
+}
+
+// Move the survivors (non-empty keys >= T) to the front of `b`, in any order; returns how many there are.
+template <int E>
+__device__ __forceinline__ int warp_store_survivors(uint64_t* b, const uint64_t (&key)[E], uint64_t T) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const bool keep = (key[e] >> 32) != 0 && key[e] >= T;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) b[base + __popc(m & lt_mask)] = key[e];
+        base += __popc(m);
+    }
+    return base;
+}
+
+template <int E>
+__device__ __forceinline__ uint64_t warp_select_compact(uint64_t* b, int k, int& kept, int grp = -1,
+                                                        const int32_t* __restrict__ group_db = nullptr) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t key[E];
+    uint32_t was = 0;  // bit e: slot e*32+lane held a candidate when it was loaded
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        key[e] = __ldcg(reinterpret_cast<const unsigned long long*>(b + e * 32 + lane));
+        was |= static_cast<uint32_t>(key[e] != 0) << e;
+    }
+    drop_same_group<E>(key, grp, group_db);
+    uint64_t kth;
+    const uint64_t T = warp_select_threshold<E>(key, k, kth);
+    kept = warp_store_survivors<E>(b, key, T);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {  // the flat kernels rely on "slots behind the candidates are zero"
+        const int pos = e * 32 + static_cast<int>(lane);
+        if (pos >= kept && ((was >> e) & 1u)) b[pos] = 0;
+    }
+    return kth;
+}
+
 // Large buffers (E > 16, i.e. k > 248): the same bitonic network, but run as loops over the buffer where it
 // lives (L2-resident global memory) instead of unrolled over registers -- a 1024..4096-key register network would
 // not fit the register file (and takes minutes to compile).  Slower per sort, but these buffers are sized >= 2k so
@@ -197,7 +308,10 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room, cons
         uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
         const int grp_l = __shfl_sync(0xffffffffu, st.grp, l);
         uint64_t kth;
-        if constexpr (E <= 16) {
+        int kept = k;
+        if constexpr (E >= 4 && E <= 16) {
+            kth = warp_select_compact<E>(b, k, kept, grp_l, group_db);
+        } else if constexpr (E <= 16) {
             uint64_t key[E];
             kth = warp_compact<E>(b, k, key, grp_l, group_db);
         } else {
@@ -205,7 +319,7 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room, cons
         }
         if (static_cast<int>(lane) == l) {
             st.thr = publish_and_refresh<strict_own>(st.gq, kth, st.thr);
-            st.cnt = st.cnt < k ? st.cnt : k;
+            st.cnt = st.cnt < kept ? st.cnt : kept;
         }
     }
     __syncwarp();

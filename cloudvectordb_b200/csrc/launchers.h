@@ -21,5 +21,9 @@ cudaError_t launch_ts2(int cfg, int E, const CUtensorMap& tx, const CUtensorMap&
                        int q_row_elems, const GemmTopkParams& p, int grid, cudaStream_t st);
 cudaError_t launch_grouped(int E, const CUtensorMap& tq, const CUtensorMap& tx, const GroupedParams& p, int grid,
                            cudaStream_t st);
+// transposed inverted-list scan (ivf_scan.cuh): list rows on the M side, <= 16 gathered queries per item, k <= 128
+struct IvfScanParams;
+cudaError_t launch_ivf_scan(const CUtensorMap& tx128, const CUtensorMap& tx32, const CUtensorMap& tq, const IvfScanParams& p,
+                            int grid, cudaStream_t st);
 
 }  // namespace cvdb
