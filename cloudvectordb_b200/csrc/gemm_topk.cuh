@@ -35,6 +35,11 @@
 #include "ptx_sm100.cuh"
 #include "topk_util.cuh"
 
+// Buffers of at least 32 * CVDB_SELECT_MIN_E slots are compacted with a select instead of a sort (A/B: -D...=99).
+#ifndef CVDB_SELECT_MIN_E
+#define CVDB_SELECT_MIN_E 4
+#endif
+
 namespace cvdb {
 
 // ---------------------------------------------------------------------------
@@ -309,7 +314,7 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room, cons
         const int grp_l = __shfl_sync(0xffffffffu, st.grp, l);
         uint64_t kth;
         int kept = k;
-        if constexpr (E >= 4 && E <= 16) {
+        if constexpr (E >= CVDB_SELECT_MIN_E && E <= 16) {
             kth = warp_select_compact<E>(b, k, kept, grp_l, group_db);
         } else if constexpr (E <= 16) {
             uint64_t key[E];

@@ -15,7 +15,7 @@ from tools.bench_ivf import clustered  # noqa: E402
 
 dev = torch.device("cuda:0")
 nprobe = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-rows, d, nlist, nq = 4_000_000, 768, 8192, 10_000
+rows, d, nlist, nq = int(os.environ.get("IVF_ROWS", 4_000_000)), 768, int(os.environ.get("IVF_NLIST", 8192)), 10_000
 g = torch.Generator(device=dev).manual_seed(99)
 centres = torch.randn((4096, d), generator=g, device=dev)
 xb = clustered(rows, d, centres, 1234)
