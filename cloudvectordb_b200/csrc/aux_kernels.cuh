@@ -150,8 +150,13 @@ __global__ void merge_partials_kernel(const uint64_t* __restrict__ part, int64_t
             }
             break;
         }
-        if (best == win) {  // keys are unique (distinct rows): exactly one lane holds the winner
-            head[bl] = static_cast<uint16_t>(head[bl] + 1);
+        // A key can sit in several lists (a slice that started from an earlier slice's result carries those keys on):
+        // every copy is at the head of its list right now, so drop them all; the owners write the same output.
+        if (best == win) {
+            for (int l = lane; l < n_lists; l += 32) {
+                const int h = head[l];
+                if (h < k_in && c[static_cast<int64_t>(l) * l_stride + h] == win) head[l] = static_cast<uint16_t>(h + 1);
+            }
             const uint32_t row = key_row(win);
             const int64_t id = ((row_ids != nullptr && row < row_ids_n) ? static_cast<int64_t>(row_ids[row])
                                                                          : static_cast<int64_t>(row)) + id_base;

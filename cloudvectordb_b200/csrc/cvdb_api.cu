@@ -598,12 +598,18 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     p.cand = ix->cand.as<uint64_t>();
     p.part = ix->part.as<uint64_t>();
     {
-        // shared thresholds [nq] and wave counters [n_waves] live in one buffer: one memset per launch
+        // shared thresholds [nq], wave counters [n_waves] and the per-item "flushed" counters [q_tiles * n_slices] live
+        // in one buffer: one memset per launch
         const int64_t n_waves = ceil_div(n_items, std::min<int64_t>(workers, n_items));
-        TRY(ix->gthr.ensure(static_cast<size_t>(nq + n_waves) * 4));
-        CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq + n_waves) * 4, st));
+        TRY(ix->gthr.ensure(static_cast<size_t>(nq + n_waves + n_items) * 4));
+        CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq + n_waves + n_items) * 4, st));
         p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
         p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->gthr.as<uint32_t>() + nq;
+        // a slice starts from the result of the latest finished earlier slice of its query tile (gemm_topk.cuh,
+        // item_begin): worth a few microseconds per item once slices are long and k > 1
+        const bool inherit = E > 0 && E <= 16 && p.n_slices > 1 && p.tiles_per_slice >= 32 && !(opts && (opts->debug_flags & 128));
+        p.done = inherit ? ix->gthr.as<uint32_t>() + nq + n_waves : nullptr;
+        p.done_full = variant == 1 ? 4 : 8;
     }
 
     // a single partial query tile on the single-CTA kernel (small, HBM-bound batches): give every epilogue warp a
@@ -691,9 +697,10 @@ int search_lists_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int
     // (list rows on the M side, <= 16 queries per item) streams every list once at HBM rate; with many pairs per
     // list the grouped kernel (128 queries per item) re-reads a list fewer times.  CVDB_IVF_KERNEL=0/1 forces one.
     const int nkb_ = static_cast<int>(ceil_div(ix->Kp, 64));
-    bool transposed = k <= 128 && nkb_ <= kIvfMaxKb && n_pairs <= 24 * static_cast<int64_t>(nlist);
+    // Measured (10M x 768, nlist 16 384, 10k queries, k = 10): 4.9 pairs per list (nprobe 8) 3.43 ms against 4.01 ms,
+    // 19.5 pairs per list (nprobe 32: two 16-query items for most lists) 9.1 ms against 7.9 ms.
+    bool transposed = k <= 128 && nkb_ <= kIvfMaxKb && n_pairs <= 10 * static_cast<int64_t>(nlist);
     if (const char* env = getenv("CVDB_IVF_KERNEL")) transposed = atoi(env) != 0 && k <= 128 && nkb_ <= kIvfMaxKb;
-    else transposed = false;  // TEMPORARY until the new kernel has passed the parity suite on the GPU
     const int item_cap = transposed ? 16 : 128;
     // --- group the (query, probe) pairs by list
     const int64_t max_items = std::min<int64_t>(nlist, n_pairs) + n_pairs / item_cap + 1;

@@ -392,10 +392,27 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
     }
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Start of a work item: reset the selection state of this thread's query.
+//
+// INHERITANCE.  A slice that starts from an empty buffer only ever learns the k-th best score of ITS OWN rows,
+// and the shared threshold gthr[q] is the best such single-slice value: with S slices every slice still collects
+// about k candidates per query, S*k in all, where a scan of the whole database with one running threshold would
+// collect ~k*ln(N/k).  At k = 200 on the headline shape that made every second 32x32 chunk take the slow
+// (candidate) path.  So an item starts from the sorted result list of the latest FINISHED earlier slice of the
+// same query tile (part[q][s'], found through the done[] counters): the buffer begins with those k keys, the
+// threshold with their k-th score, and what the item writes at its end is the top-k of everything the chain has
+// seen.  The lists of different slices then overlap; the final merge drops the copies (a key present in several
+// lists reaches the head of all of them in the same round).  Results do not depend on which slice, if any, was
+// inherited.
 template <int E>
 __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams& p, int q_row, bool q_valid,
-                                           uint64_t* warp_buf) {
+                                           uint64_t* warp_buf, int qt = 0, int slice = 0) {
     constexpr int C = 32 * (E > 0 ? E : 1);
     const uint32_t lane = threadIdx.x & 31;
     st.gq = (q_valid && p.gthr != nullptr) ? p.gthr + q_row : nullptr;
@@ -403,8 +420,38 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
     st.thr = !q_valid ? INFINITY : (st.gq ? thr_from_shared(__ldcg(st.gq)) : -INFINITY);
     if constexpr (E > 0) {
         st.cnt = 0;
-        for (int i = lane; i < 32 * C; i += 32) warp_buf[i] = 0;  // the warp's 32 buffers are contiguous
-        __syncwarp();
+        int src = -1;
+        if (E <= 16 && p.done != nullptr) {  // warp-uniform: every lane reads the same counters
+            const uint32_t* d = p.done + static_cast<size_t>(qt) * p.n_slices;
+            for (int s = slice - 1; s >= 0 && s >= slice - 4; --s)
+                if (ld_acquire_u32(d + s) >= static_cast<uint32_t>(p.done_full)) { src = s; break; }
+        }
+        if (src < 0) {
+            for (int i = lane; i < 32 * C; i += 32) warp_buf[i] = 0;  // the warp's 32 buffers are contiguous
+            __syncwarp();
+        } else {
+            const int k = p.k;
+            for (int l = 0; l < 32; ++l) {
+                const int ql = __shfl_sync(0xffffffffu, q_row, l);
+                const bool vl = __shfl_sync(0xffffffffu, static_cast<int>(q_valid), l) != 0;
+                const uint64_t* from = p.part + (static_cast<size_t>(vl ? ql : 0) * p.n_slices + src) * k;
+                uint64_t* b = warp_buf + static_cast<size_t>(l) * C;
+                int n = 0;
+#pragma unroll
+                for (int e = 0; e < (E > 0 ? E : 1); ++e) {
+                    const int pos = e * 32 + static_cast<int>(lane);
+                    const uint64_t key = (vl && pos < k) ? __ldcg(reinterpret_cast<const unsigned long long*>(from + pos)) : 0ull;
+                    b[pos] = key;
+                    n += __popc(__ballot_sync(0xffffffffu, key != 0));
+                }
+                if (static_cast<int>(lane) == l) st.cnt = n;
+            }
+            __syncwarp();
+            if (st.cnt >= k) {  // a full list: its k-th score bounds what can still enter (equal scores stay candidates)
+                const uint64_t kth = __ldcg(reinterpret_cast<const unsigned long long*>(st.buf + k - 1));
+                st.thr = fmaxf(st.thr, thr_from_shared(static_cast<uint32_t>(kth >> 32)));
+            }
+        }
     } else {
         st.best = 0;
     }
@@ -433,7 +480,7 @@ __device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* ou
 // End of a work item: sorted top-k of every query of the warp -> part[q][slice][0..k).
 template <int E>
 __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams& p, int q_base, int q_row, bool q_valid,
-                                           int slice, int q_lanes = 32) {
+                                           int slice, int q_lanes = 32, int qt = 0) {
     const uint32_t lane = threadIdx.x & 31;
     if constexpr (E > 0) {
         __syncwarp();
@@ -471,6 +518,11 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
                     out[pos] = __ldcg(reinterpret_cast<const unsigned long long*>(b + pos));
             }
             if (static_cast<int>(lane) == l && kth != 0 && st.gq != nullptr) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
+        }
+        if (p.done != nullptr) {  // this warp's lists of the item are in part[]: later slices may start from them
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(p.done + static_cast<size_t>(qt) * p.n_slices + slice, 1u);
         }
         __syncwarp();
     } else {
@@ -636,7 +688,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const bool q_valid = static_cast<int>(lane) < q_lanes && q_row < p.nq;
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
-            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C);
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32) * C, qt, slice);
             if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
@@ -661,7 +713,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            item_flush<E>(st, p, q_base, q_row, q_valid, slice, q_lanes);
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice, q_lanes, qt);
         }
     }
 
@@ -1224,7 +1276,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
-            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C, qt, slice);
             if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
@@ -1249,7 +1301,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            item_flush<E>(st, p, q_base, q_row, q_valid, slice);
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice, 32, qt);
         }
     }
 
@@ -1419,7 +1471,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const bool q_valid = q_row < p.nq;
             const uint32_t self = (p.self_ids && q_valid) ? static_cast<uint32_t>(__ldg(p.self_ids + q_row)) : 0xFFFFFFFFu;
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
-            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C);
+            item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C, qt, slice);
             if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
@@ -1444,7 +1496,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            item_flush<E>(st, p, q_base, q_row, q_valid, slice);
+            item_flush<E>(st, p, q_base, q_row, q_valid, slice, 32, qt);
         }
     }
 

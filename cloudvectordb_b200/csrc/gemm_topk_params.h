@@ -28,6 +28,8 @@ struct GemmTopkParams {
     uint64_t* part;  // [nq][n_slices][k] per-slice results (keys)
     uint32_t* gthr;  // [nq] shared per-query threshold (ordered-float), zeroed before the launch
     uint32_t* wave_cnt;  // [waves] producers that finished issuing the loads of their item in that wave (or null)
+    uint32_t* done;      // [q_tiles][n_slices] epilogue warps that have flushed that item (zeroed; null: no inheritance)
+    int done_full;       // warps that flush one item: 4 (single CTA) or 8 (CTA pair)
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
     int a_quarter;   // single-CTA kernel with one partial query tile: query rows per epilogue warp (the A tile is
                      // loaded as four 32-row boxes, box j = queries [j*a_quarter, j*a_quarter + 32)); 0 = one box

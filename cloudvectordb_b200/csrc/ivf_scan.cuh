@@ -73,6 +73,27 @@ __device__ __forceinline__ bool epi_barrier_or(bool pred) {
     return r != 0;
 }
 
+// Sort the first n (<= 32*ES) keys of a shared-memory buffer (warp-cooperative) and write the k output entries
+// (missing ones as 0).  Returns the k-th best key (0 when fewer than k candidates exist).
+template <int ES>
+__device__ __forceinline__ uint64_t flush_sorted(const uint64_t* b, int n, uint64_t* out, int k) {
+    const int lane = threadIdx.x & 31;
+    uint64_t key[ES];
+#pragma unroll
+    for (int e = 0; e < ES; ++e) {
+        const int pos = e * 32 + lane;
+        key[e] = pos < n ? b[pos] : 0;
+    }
+    warp_bitonic_sort_desc<ES>(key);
+#pragma unroll
+    for (int e = 0; e < ES; ++e) {
+        const int pos = e * 32 + lane;
+        if (pos < k) out[pos] = key[e];
+    }
+    for (int pos = 32 * ES + lane; pos < k; pos += 32) out[pos] = 0;
+    return k <= 32 * ES ? warp_sorted_at<ES>(key, k - 1) : 0;
+}
+
 template <int NQ, int STAGES>
 constexpr size_t ivf_scan_smem_bytes() {
     return 1024 + size_t(STAGES) * 16384 + 2 * size_t(kIvfMaxKb) * NQ * 128 + size_t(NQ) * kIvfCap * 8 +
@@ -362,20 +383,16 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmap_x128, const __grid_cons
                 if (dst < 0) continue;  // warp-uniform
                 const uint64_t* b = cand + q * kIvfCap;
                 const int cn = cnt_s[q];
-                uint64_t key[kIvfCap / 32];
-#pragma unroll
-                for (int e = 0; e < kIvfCap / 32; ++e) {
-                    const int pos = e * 32 + static_cast<int>(lane);
-                    key[e] = pos < cn ? b[pos] : 0;
-                }
-                warp_bitonic_sort_desc<kIvfCap / 32>(key);
                 uint64_t* out = p.part + static_cast<size_t>(dst) * k;
-#pragma unroll
-                for (int e = 0; e < kIvfCap / 32; ++e) {
-                    const int pos = e * 32 + static_cast<int>(lane);
-                    if (pos < k) out[pos] = key[e];
+                uint64_t kth;
+                // a buffer usually holds a few dozen candidates when its list ends: sort only what is there
+                if (cn <= 32) {
+                    kth = flush_sorted<1>(b, cn, out, k);
+                } else if (cn <= 64) {
+                    kth = flush_sorted<2>(b, cn, out, k);
+                } else {
+                    kth = flush_sorted<kIvfCap / 32>(b, cn, out, k);
                 }
-                const uint64_t kth = warp_sorted_at<kIvfCap / 32>(key, k - 1);
                 if (lane == 0 && kth != 0) atomicMax(p.gthr + query_s[q], static_cast<uint32_t>(kth >> 32));
             }
             epi_barrier();  // nobody resets the per-query state while another warp still flushes

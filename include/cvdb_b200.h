@@ -76,7 +76,8 @@ typedef struct cvdb_search_opts {
                                 8 = no wave alignment of the producers, 16 = run all K-steps of the padded row width,
                                 32 = always sort the whole candidate buffer at the end of a work item,
                                 64 = small batches: fill the query tile from row 0 up instead of one quarter per
-                                epilogue warp (4, 8, 16, 32 and 64 leave the results valid) */
+                                epilogue warp, 128 = every database slice starts from an empty candidate buffer instead
+                                of the result of an earlier slice (4, 8, 16, 32, 64 and 128 leave the results valid) */
 } cvdb_search_opts;
 
 /* -- index lifetime -------------------------------------------------------

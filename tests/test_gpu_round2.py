@@ -278,3 +278,37 @@ def test_handleless_calls_run_on_the_device_that_owns_the_data():
     assert torch.equal(Im.cpu(), torch.from_numpy(I_ref))
     assert torch.cuda.current_device() == 0
     ivf.close()
+
+
+# ---- slices that start from an earlier slice's result (inheritance) ---------------------------------------------
+@pytest.mark.parametrize("variant,k", [(1, 10), (2, 50), (3, 100), (2, 200), (1, 20)])
+def test_slice_inheritance_is_result_neutral(variant, k):
+    """Many database slices (more than 32, so merge lanes own several lists), slices long enough to inherit: the
+    lists of different slices overlap and the merge must drop the copies.  Same answer with inheritance off
+    (debug flag 128), and equal to the oracle; with exclusion as well."""
+    from cloudvectordb_b200 import IndexFlat
+    rng = np.random.default_rng(variant * 100 + k)
+    n, d, nq = 400_000, 64, 300
+    xb = O.bf16_round(unit_rows(rng, n, d))
+    xb[1000:1040] = xb[7]                                   # a block of exact duplicates (ties across and inside slices)
+    xb[390_000:390_020] = xb[7]
+    xq = O.bf16_round(unit_rows(rng, nq, d))
+    xq[0] = xb[7]
+    idx = IndexFlat(d, "ip", "bf16", 0)
+    idx.add(xb)
+    slices = 40 if variant != 1 else 45
+    D, I = idx.search(xq, k, force_variant=variant, force_slices=slices)
+    assert idx.last_work()["n_slices"] >= 33
+    D0, I0 = idx.search(xq, k, force_variant=variant, force_slices=slices, debug_flags=128)
+    assert np.array_equal(I, I0) and np.array_equal(D, D0)
+    D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_IP)
+    assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
+    assert all(len(set(r[r >= 0])) == (r >= 0).sum() for r in I)           # no id twice
+    groups = (np.arange(n) // 4).astype(np.int32)
+    idx.set_groups(groups)
+    self_ids = rng.integers(0, n, nq).astype(np.int32)
+    gq = groups[self_ids]
+    D, I = idx.search(xb[self_ids], k, self_ids=self_ids, group_q=gq, force_variant=variant, force_slices=slices)
+    D_ref, I_ref = O.search_ref(xb, xb[self_ids], k, O.METRIC_IP, self_ids=self_ids, group_db=groups, group_q=gq)
+    assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
+    idx.close()

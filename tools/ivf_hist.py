@@ -75,6 +75,22 @@ def main():
                     ts.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
                 rec[f"kernel{kern}_probe_ms"] = float(np.median([t[0] for t in ts]))
                 rec[f"kernel{kern}_search_ms_incl_probe"] = float(np.median([t[1] for t in ts]))
+            # the coarse search alone, per kernel variant (10k queries x nlist centroids, k = nprobe)
+            for v in (0, 1, 2, 3):
+                try:
+                    for _ in range(2):
+                        ivf.quantizer.search(xq, nprobe, force_variant=v)
+                    torch.cuda.synchronize()
+                    ev[0].record()
+                    for _ in range(5):
+                        ivf.quantizer.search(xq, nprobe, force_variant=v, profile=True)
+                    ev[1].record()
+                    torch.cuda.synchronize()
+                    rec[f"coarse_variant{v}_ms"] = ev[0].elapsed_time(ev[1]) / 5
+                    rec[f"coarse_variant{v}_kernel_ms"] = float(np.median(ivf.quantizer.profile_ms()))
+                    rec[f"coarse_variant{v}_used"] = ivf.quantizer.last_work()
+                except Exception as e:
+                    rec[f"coarse_variant{v}_error"] = str(e)[:80]
             line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")
