@@ -74,6 +74,11 @@ SIGNATURES = {
                                          C.POINTER(SearchOpts), C.c_void_p]),
     "cvdb_index_merge_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "cvdb_selfjoin_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cvdb_selfjoin_chunk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cvdb_selfjoin_finish": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvdb_selfjoin_dirty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "cvdb_selfjoin_end": (C.c_int, [C.c_void_p]),
     "cvdb_kmeans_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
     "cvdb_kmeans_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

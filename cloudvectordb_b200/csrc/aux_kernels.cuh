@@ -378,6 +378,11 @@ __global__ void ivf_scatter_rows_kernel(const int32_t* __restrict__ list_of_id, 
     for (int c = lane; c < row_vec16; c += 32) dst[c] = src[c];
 }
 
+__global__ void fill_f32_kernel(float* __restrict__ out, int64_t n, float v) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
 __global__ void iota_kernel(int32_t* __restrict__ out, int64_t first, int64_t n) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = static_cast<int32_t>(first + i);
@@ -507,6 +512,103 @@ __global__ void build_triplets_kernel(const int64_t* __restrict__ I, const float
         }
     }
     for (; w < per_anchor; ++w) { o[3 * w] = -1; o[3 * w + 1] = -1; o[3 * w + 2] = -1; }
+}
+
+// ---------------------------------------------------------------------------
+// Symmetric self-join, column direction (gemm_topk.cuh, scan_chunk_col): per database row a buffer of
+// kColCap keys, the first col_base[r] of which are the survivors of the previous compaction.
+// col_compact: one warp per row that received candidates since then: drop same-group candidates, keep the best
+// k (select, not sort), publish the row's new threshold.  A row whose counter ran past the buffer lost
+// candidates: it is flagged dirty (the caller recomputes it exactly) and stops collecting.
+// ---------------------------------------------------------------------------
+constexpr int kColCap = 256;
+
+__global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __restrict__ col_cnt,
+                                   uint32_t* __restrict__ col_base, float* __restrict__ col_thr,
+                                   uint8_t* __restrict__ dirty, int k, int64_t row_min, int64_t n_rows,
+                                   const int32_t* __restrict__ group_db) {
+    constexpr int E = kColCap / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = row_min + warp0; r < n_rows; r += nwarps) {
+        const uint32_t cnt = col_cnt[r];
+        if (cnt == col_base[r]) continue;  // nothing new (warp-uniform)
+        if (cnt > static_cast<uint32_t>(kColCap)) {
+            if (lane == 0) {
+                dirty[r] = 1;
+                col_thr[r] = INFINITY;
+                col_base[r] = cnt;
+            }
+            continue;
+        }
+        uint64_t* b = col_buf + r * kColCap;
+        uint64_t key[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const uint32_t pos = e * 32 + lane;
+            key[e] = pos < cnt ? b[pos] : 0;
+        }
+        if (group_db != nullptr) {
+            const int grp = group_db[r];
+            if (grp >= 0) {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (key[e] != 0 && group_db[key_row(key[e])] == grp) key[e] = 0;
+            }
+        }
+        uint64_t kth;
+        const uint64_t T = warp_select_threshold<E>(key, k, kth);
+        const int kept = warp_store_survivors<E>(b, key, T);
+        if (lane == 0) {
+            col_cnt[r] = kept;
+            col_base[r] = kept;
+            const uint32_t ord = static_cast<uint32_t>(kth >> 32);
+            // equal scores stay candidates (the key decides): one step below the k-th score
+            if (ord != 0) col_thr[r] = ord == 0x80000000u ? -1.17549435e-38f : ordered_to_float(ord - 1u);
+        }
+    }
+}
+
+// Final answer of anchor i = top-k of (its row-direction keys, sorted, k of them) and (its column list, <= k keys,
+// unsorted).  The two sets are disjoint (rows at or after the anchor's chunk / anchors of earlier chunks).
+// One warp per anchor; k <= 124.
+__global__ void selfjoin_finalize_kernel(const uint64_t* __restrict__ row_keys, const uint64_t* __restrict__ col_buf,
+                                         const uint32_t* __restrict__ col_cnt, int64_t row0, int64_t n, int k,
+                                         float* __restrict__ D, int64_t* __restrict__ I) {
+    constexpr int E = 8;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const uint32_t nc = min(col_cnt[row0 + i], static_cast<uint32_t>(k));
+    uint64_t key[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int pos = e * 32 + lane;
+        uint64_t v = 0;
+        if (pos < k) v = row_keys[i * k + pos];
+        else if (pos - k < static_cast<int>(nc)) v = col_buf[(row0 + i) * kColCap + (pos - k)];
+        key[e] = v;
+    }
+    warp_bitonic_sort_desc<E>(key);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int pos = e * 32 + lane;
+        if (pos < k) {
+            const uint64_t v = key[e];
+            D[i * k + pos] = v != 0 ? key_score(v) : -INFINITY;
+            I[i * k + pos] = v != 0 ? static_cast<int64_t>(key_row(v)) : -1;
+        }
+    }
+}
+
+// rows flagged dirty -> compact list (order unspecified)
+__global__ void collect_flagged_kernel(const uint8_t* __restrict__ flag, int64_t n, int32_t* __restrict__ out,
+                                       int64_t max_out, unsigned long long* __restrict__ count) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const unsigned long long pos = atomicAdd(count, 1ull);
+    if (static_cast<int64_t>(pos) < max_out) out[pos] = static_cast<int32_t>(i);
 }
 
 // Exact-mode rescoring: recompute the score of each returned row from the

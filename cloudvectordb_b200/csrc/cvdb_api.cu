@@ -155,6 +155,10 @@ struct Index {
     DevBuf row_ids, list_off, ivf_cnt, ivf_pair_off, ivf_item_off, ivf_cursor, ivf_scal, ivf_items, ivf_pair_query,
         ivf_pair_dst, ivf_qg, ivf_probes;
     DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
+    // symmetric self-join state (cvdb_selfjoin_*): per database row a threshold, a counter, the survivors' count
+    // and a buffer of kColCap keys for the column direction; sj_k > 0 while a join is open
+    DevBuf col_thr, col_cnt, col_base, col_buf, col_dirty, col_scal;
+    int sj_k = 0;
     DevBuf bad_rows;  // one uint64: rows (added or queried) whose squared norm was not finite
     bool has_groups = false;
     // Rows re-stored list-major keep their caller-visible ids in row_ids: every id leaving the library is
@@ -492,11 +496,21 @@ void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& 
 
 // Core: search `nq` packed-on-the-fly queries against the whole index.
 // Outputs are device pointers: D [nq][k] f32 and either I64 or I32 [nq][k].
+// What the symmetric self-join adds to a search: the queries ARE packed rows of the index (no packing pass),
+// only database rows from row_begin on are scanned, and every score is also offered to its database row.
+struct SearchExtra {
+    const __nv_bfloat16* q_packed = nullptr;  // packed query rows (nq of them used)
+    int64_t q_rows_avail = 0;                 // rows readable from q_packed on
+    int64_t row_begin = 0;                    // first database row scanned (multiple of 128)
+    bool col = false;                         // column direction on (Index::col_*)
+    int64_t col_row_min = 0;                  // database rows below this do not collect
+};
+
 // `keys_out` (optional, instead of D/I): the merged top-k as keys carrying the caller's ids (shard exchange).
 // `q_norm`: where the squared norms of the packed queries go ([nq] f32, device).
 int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, float* D, int64_t* I64, int32_t* I32,
                   const int32_t* self_ids, const int32_t* group_q, const cvdb_search_opts* opts, cudaStream_t st,
-                  uint64_t* keys_out = nullptr, float* q_norm = nullptr) {
+                  uint64_t* keys_out = nullptr, float* q_norm = nullptr, const SearchExtra* ex = nullptr) {
     const int E = pick_E(k);
     const int C = 32 * (E ? E : 1);
     const int l2 = ix->metric == CVDB_METRIC_L2;
@@ -505,12 +519,20 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     // the packed query matrix is padded with zero rows to a whole 256-query tile, so the A-operand
     // TMA boxes never run out of bounds (partially out-of-bounds boxes load measurably slower)
     const int64_t nq_pad = ceil_div(nq, 256) * 256;
-    TRY(ix->q_pack.ensure(static_cast<size_t>(nq_pad) * ix->row_elems * 2));
     if (!q_norm) {
         TRY(ix->q_norm.ensure(static_cast<size_t>(nq) * 4));
         q_norm = ix->q_norm.as<float>();
     }
-    TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, q_norm, st, nq_pad));
+    const __nv_bfloat16* q_rows = nullptr;  // the packed queries
+    int64_t q_rows_n = nq_pad;              // rows the query tensor map covers
+    if (ex && ex->q_packed) {
+        q_rows = ex->q_packed;
+        q_rows_n = std::min(nq_pad, ex->q_rows_avail);
+    } else {
+        TRY(ix->q_pack.ensure(static_cast<size_t>(nq_pad) * ix->row_elems * 2));
+        TRY(pack_dispatch(q_dev, dtype, nq, ix->q_pack.as<__nv_bfloat16>(), ix, 1, q_norm, st, nq_pad));
+        q_rows = ix->q_pack.as<__nv_bfloat16>();
+    }
     const int32_t* row_ids = ix->permuted() ? ix->row_ids.as<int32_t>() : nullptr;
 
     if (ix->ntotal == 0) {
@@ -568,25 +590,31 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         if (!(ts2_ok && p.nkb <= 12)) return fail(CVDB_EINVAL, "variant 4 needs bf16 storage and padded d <= 768");
         variant = 4;
     }
+    if (ex && (ex->col || ex->row_begin > 0)) {
+        if (!(ts2_ok && p.nkb <= 12)) return fail(CVDB_EINVAL, "the symmetric self-join needs bf16 storage and padded d <= 768");
+        variant = 2;
+    }
     const bool resident = variant == 2 || variant == 4;
     const int block_n = !resident ? kBlockN : (variant == 4 ? 64 : 128);
     const int q_tile = variant == 1 ? 128 : 256;
     const int sms = ix->num_sms;
     const int workers = variant == 1 ? sms : sms / 2;  // CTAs or CTA pairs
     p.q_tiles = static_cast<int>(ceil_div(nq, q_tile));
-    p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, block_n));
+    p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, block_n));  // END tile of the scan
+    p.tile0 = ex ? static_cast<int>(ex->row_begin / block_n) : 0;
+    const int scan_tiles = p.n_tiles - p.tile0;
     // keep the per-slice result scratch under ~1 GiB
     const int64_t max_slices = std::max<int64_t>(1, (int64_t(1) << 30) / std::max<int64_t>(1, nq * k * 8));
     if (opts && opts->force_slices > 0) {
-        const int64_t s = std::min<int64_t>(opts->force_slices, p.n_tiles);
-        p.tiles_per_slice = static_cast<int>(ceil_div(p.n_tiles, s));
-        p.n_slices = static_cast<int>(ceil_div(p.n_tiles, p.tiles_per_slice));
+        const int64_t s = std::min<int64_t>(opts->force_slices, scan_tiles);
+        p.tiles_per_slice = static_cast<int>(ceil_div(scan_tiles, s));
+        p.n_slices = static_cast<int>(ceil_div(scan_tiles, p.tiles_per_slice));
     } else {
         // per-item overhead in tile times: the resident-query kernel reloads its queries into TMEM and drains
         // the pipeline at every item boundary (~10 us), the streaming kernels only flush their results
         int ovh = (variant == 2 || variant == 4) ? 8 : 4;
         if (const char* env = getenv("CVDB_PLAN_OVH")) ovh = atoi(env);  // tuning experiments
-        choose_slices(p.q_tiles, p.n_tiles, workers, max_slices, p.n_slices, p.tiles_per_slice, ovh);
+        choose_slices(p.q_tiles, scan_tiles, workers, max_slices, p.n_slices, p.tiles_per_slice, ovh);
     }
     const int64_t n_items = static_cast<int64_t>(p.q_tiles) * p.n_slices;
     const int grid = static_cast<int>(std::min<int64_t>(workers, n_items)) * (variant == 1 ? 1 : 2);
@@ -616,7 +644,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     // quarter of the queries instead of filling the TMEM lanes from 0 up, where 32 queries are one warp's work
     p.a_quarter = (variant == 1 && nq < 128 && !(opts && (opts->debug_flags & 64))) ? static_cast<int>(ceil_div(nq, 4)) : 0;
     CUtensorMap tq, tx;
-    TRY(get_tmap(ix->tm_q, &tq, ix->q_pack.p, nq_pad, ix->row_elems, p.a_quarter > 0 ? 32 : 128));
+    TRY(get_tmap(ix->tm_q, &tq, q_rows, q_rows_n, ix->row_elems, p.a_quarter > 0 ? 32 : 128));
     TRY(get_tmap(ix->tm_x, &tx, ix->x, ix->ntotal, ix->row_elems, variant == 1 ? kBlockN : block_n / 2));
 
     const bool prof = opts && opts->profile;
@@ -629,10 +657,19 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         CU_TRY(cudaEventRecord(ix->ev0[slot], st));
     }
     if (variant == 4) {
-        LAUNCH(launch_ts2(3, E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st));
+        LAUNCH(launch_ts2(3, E, tx, tq, q_rows, ix->row_elems, p, grid, st));
     } else if (variant == 2) {
         const int cfg = p.nkb <= 8 ? 0 : (p.nkb <= 12 ? 1 : 2);  // all of K in TMEM / + 4-block tail / + 5-block tail
-        LAUNCH(launch_ts2(cfg, E, tx, tq, ix->q_pack.as<__nv_bfloat16>(), ix->row_elems, p, grid, st));
+        if (ex && ex->col) {
+            p.col_thr = ix->col_thr.as<float>();
+            p.col_cnt = ix->col_cnt.as<uint32_t>();
+            p.col_buf = ix->col_buf.as<uint64_t>();
+            p.col_cap = kColCap;
+            p.col_row_min = static_cast<int>(ex->col_row_min);
+            LAUNCH(launch_ts2_col(cfg, E, tx, tq, q_rows, ix->row_elems, p, grid, st));
+        } else {
+            LAUNCH(launch_ts2(cfg, E, tx, tq, q_rows, ix->row_elems, p, grid, st));
+        }
     } else if (variant == 3) {
         LAUNCH(launch_ss2(E, tq, tx, p, grid, st));
     } else {
@@ -643,8 +680,9 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         ix->prof_head = (slot + 1) % Index::kProfSlots;
         ix->prof_count = std::min(ix->prof_count + 1, Index::kProfSlots);
     }
-    ix->last_flops = 2.0 * double(nq) * double(ix->ntotal) * double(ix->d);
-    ix->last_bytes = double(ix->ntotal) * double(ix->row_elems) * 2.0;
+    const double rows_scanned = double(ix->ntotal) - (ex ? double(ex->row_begin) : 0.0);
+    ix->last_flops = 2.0 * double(nq) * rows_scanned * double(ix->d);
+    ix->last_bytes = rows_scanned * double(ix->row_elems) * 2.0;
     ix->last_slices = p.n_slices;
     ix->last_grid = grid;
     ix->last_variant = variant;
@@ -864,6 +902,7 @@ int cvdb_index_destroy(cvdb_index_t h) {
     for (DevBuf* b : {&ix->row_ids, &ix->list_off, &ix->ivf_cnt, &ix->ivf_pair_off, &ix->ivf_item_off, &ix->ivf_cursor,
                       &ix->ivf_scal, &ix->ivf_items, &ix->ivf_pair_query, &ix->ivf_pair_dst, &ix->ivf_qg, &ix->ivf_probes})
         b->release();
+    for (DevBuf* b : {&ix->col_thr, &ix->col_cnt, &ix->col_base, &ix->col_buf, &ix->col_dirty, &ix->col_scal}) b->release();
     for (DevBuf* b : {&ix->gthr, &ix->waves, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
                       &ix->ids_b, &ix->groups, &ix->bad_rows})
         b->release();
@@ -1332,6 +1371,119 @@ int cvdb_merge_topk(const float* Dc, const int64_t* Ic, int64_t nq, int nlists, 
     const cudaError_t es = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = ef != cudaSuccess ? ef : es;
     if (e != cudaSuccess) return fail(CVDB_ECUDA, "merge failed: %s", cudaGetErrorString(e));
+    return CVDB_OK;
+}
+
+// ------------------------------------------------------------ symmetric self-join
+int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->metric != CVDB_METRIC_IP || ix->planes != 1)
+        return fail(CVDB_EINVAL, "the symmetric self-join needs an inner-product index with bf16 storage");
+    if (ceil_div(ix->Kp, 64) > 12) return fail(CVDB_ELIMIT, "the symmetric self-join needs padded d <= 768");
+    if (k < 2 || k > 124) return fail(CVDB_ELIMIT, "k=%d outside [2, 124]", k);
+    if (ix->permuted()) return fail(CVDB_EINVAL, "rows are stored list-major: ids and stored positions differ");
+    if (ix->ntotal < 1) return fail(CVDB_EINVAL, "empty index");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    const size_t n = static_cast<size_t>(ix->ntotal);
+    TRY(ix->col_thr.ensure(n * 4));
+    TRY(ix->col_cnt.ensure(n * 4));
+    TRY(ix->col_base.ensure(n * 4));
+    TRY(ix->col_dirty.ensure(n));
+    TRY(ix->col_scal.ensure(16));
+    TRY(ix->col_buf.ensure(n * kColCap * 8));
+    CU_TRY(cudaMemsetAsync(ix->col_cnt.p, 0, n * 4, st));
+    CU_TRY(cudaMemsetAsync(ix->col_base.p, 0, n * 4, st));
+    CU_TRY(cudaMemsetAsync(ix->col_dirty.p, 0, n, st));
+    fill_f32_kernel<<<static_cast<unsigned>(ceil_div(ix->ntotal, 256)), 256, 0, st>>>(ix->col_thr.as<float>(), ix->ntotal, -INFINITY);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    ix->sj_k = k;
+    return CVDB_OK;
+}
+
+int cvdb_selfjoin_chunk(cvdb_index_t h, int64_t row0, int64_t nrows, uint64_t* keys, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
+    if (row0 < 0 || nrows < 1 || row0 + nrows > ix->ntotal) return fail(CVDB_EINVAL, "anchor rows outside the index");
+    if (row0 % 128) return fail(CVDB_EINVAL, "row0 must be a multiple of 128 (the scan starts at a tile boundary)");
+    if (nrows > 65536) return fail(CVDB_ELIMIT, "at most 65536 anchors per chunk");
+    if (!keys) return fail(CVDB_EINVAL, "null pointer");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    const int k = ix->sj_k;
+    TRY(ix->ids_a.ensure(static_cast<size_t>(nrows) * 4));
+    iota_kernel<<<static_cast<unsigned>(ceil_div(nrows, 256)), 256, 0, st>>>(ix->ids_a.as<int32_t>(), row0, nrows);
+    ++g_launches;
+    SearchExtra ex;
+    ex.q_packed = ix->x + row0 * ix->row_elems;
+    ex.q_rows_avail = ix->ntotal - row0;
+    ex.row_begin = row0;
+    ex.col = true;
+    ex.col_row_min = row0 + nrows;
+    const int32_t* grp = ix->has_groups ? ix->groups.as<int32_t>() + row0 : nullptr;
+    TRY(search_device(ix, nullptr, nrows, CVDB_DTYPE_BF16, k, nullptr, nullptr, nullptr, ix->ids_a.as<int32_t>(), grp, nullptr, st,
+                      keys, nullptr, &ex));
+    if (row0 + nrows < ix->ntotal) {
+        const int64_t m = ix->ntotal - (row0 + nrows);
+        const int64_t blocks = std::min<int64_t>(ceil_div(m, 8), 148 * 32);
+        col_compact_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(), ix->col_base.as<uint32_t>(), ix->col_thr.as<float>(),
+            ix->col_dirty.as<uint8_t>(), k, row0 + nrows, ix->ntotal, ix->has_groups ? ix->groups.as<int32_t>() : nullptr);
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+    }
+    return CVDB_OK;
+}
+
+int cvdb_selfjoin_finish(cvdb_index_t h, int64_t row0, int64_t nrows, const uint64_t* row_keys, float* D, int64_t* I,
+                         void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > ix->ntotal) return fail(CVDB_EINVAL, "rows outside the index");
+    if (nrows == 0) return CVDB_OK;
+    if (!row_keys || !D || !I) return fail(CVDB_EINVAL, "null pointer");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    selfjoin_finalize_kernel<<<static_cast<unsigned>(ceil_div(nrows, 8)), 256, 0, st>>>(
+        row_keys, ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(), row0, nrows, ix->sj_k, D, I);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+
+int cvdb_selfjoin_dirty(cvdb_index_t h, int32_t* rows_out, int64_t max_out, int64_t* n_out, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
+    if (!n_out || max_out < 0 || (max_out > 0 && !rows_out)) return fail(CVDB_EINVAL, "bad arguments");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    CU_TRY(cudaMemsetAsync(ix->col_scal.p, 0, 8, st));
+    collect_flagged_kernel<<<static_cast<unsigned>(ceil_div(ix->ntotal, 256)), 256, 0, st>>>(
+        ix->col_dirty.as<uint8_t>(), ix->ntotal, rows_out, max_out, ix->col_scal.as<unsigned long long>());
+    ++g_launches;
+    unsigned long long c = 0;
+    CU_TRY(cudaMemcpyAsync(&c, ix->col_scal.p, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *n_out = static_cast<int64_t>(c);
+    return CVDB_OK;
+}
+
+int cvdb_selfjoin_end(cvdb_index_t h) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    cvdb_guard g(ix->device);
+    cudaDeviceSynchronize();
+    ix->sj_k = 0;
+    for (DevBuf* b : {&ix->col_thr, &ix->col_cnt, &ix->col_base, &ix->col_buf, &ix->col_dirty}) b->release();
     return CVDB_OK;
 }
 

@@ -157,84 +157,6 @@ __device__ __forceinline__ uint64_t warp_compact(uint64_t* b, int k, uint64_t (&
 // stages -- a sort used to hold its epilogue warp for more than two MMA tiles, i.e. it stalled the tensor pipe.
 // Returns a key whose score word is the k-th best score (0 when fewer than k candidates exist); `kept` = number of
 // survivors now at the front of the buffer (slots behind them are zero).
-// The select itself, on keys held in registers (slot e*32+lane in key[e], 0 = empty): returns T such that the
-// survivors are exactly the non-empty keys >= T (the best k, or all of them when there are at most k), and sets
-// kth to a key whose score word is the k-th best score (0 when fewer than k candidates exist).
-template <int E>
-__device__ __forceinline__ uint64_t warp_select_threshold(const uint64_t (&key)[E], int k, uint64_t& kth) {
-    constexpr unsigned kFull = 0xffffffffu;
-    uint32_t hi[E];
-    int my_valid = 0;
-    uint32_t mx = 0, mn = 0xFFFFFFFFu;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        hi[e] = static_cast<uint32_t>(key[e] >> 32);  // 0 <=> empty slot (the score word of a real candidate is never 0)
-        my_valid += hi[e] != 0;
-        mx = max(mx, hi[e]);
-        mn = hi[e] != 0 ? min(mn, hi[e]) : mn;
-    }
-    const int n_valid = __reduce_add_sync(kFull, my_valid);
-    mx = __reduce_max_sync(kFull, mx);
-    mn = __reduce_min_sync(kFull, mn);
-    kth = 0;
-    if (n_valid <= k) {  // warp-uniform
-        if (n_valid == k) kth = (static_cast<uint64_t>(mn) << 32) | 1u;
-        return 1;  // keep every candidate
-    }
-    uint32_t prefix = mx;
-    const uint32_t diff = mx ^ mn;
-    if (diff != 0) {
-        int bit = 31 - __clz(diff);
-        prefix = mx & ~((2u << bit) - 1u);  // the bits every candidate shares
-        for (; bit >= 0; --bit) {
-            const uint32_t trial = prefix | (1u << bit);
-            int c = 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) c += hi[e] >= trial;
-            if (__reduce_add_sync(kFull, c) >= k) prefix = trial;
-        }
-    }
-    // prefix == the k-th largest score word
-    int c_gt = 0, c_eq = 0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        c_gt += hi[e] > prefix;
-        c_eq += hi[e] == prefix;
-    }
-    c_gt = __reduce_add_sync(kFull, c_gt);
-    c_eq = __reduce_add_sync(kFull, c_eq);
-    const int need = k - c_gt;  // how many of the rows tied at the k-th score stay: the lowest ids
-    uint32_t low = 0;
-    if (need < c_eq) {
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t trial = low | (1u << bit);
-            int c = 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) c += (hi[e] == prefix) && (static_cast<uint32_t>(key[e]) >= trial);
-            if (__reduce_add_sync(kFull, c) >= need) low = trial;
-        }
-    }
-    const uint64_t T = (static_cast<uint64_t>(prefix) << 32) | low;
-    kth = T | 1u;
-    return T;
-}
-
-// Move the survivors (non-empty keys >= T) to the front of `b`, in any order; returns how many there are.
-template <int E>
-__device__ __forceinline__ int warp_store_survivors(uint64_t* b, const uint64_t (&key)[E], uint64_t T) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    int base = 0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const bool keep = (key[e] >> 32) != 0 && key[e] >= T;
-        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) b[base + __popc(m & lt_mask)] = key[e];
-        base += __popc(m);
-    }
-    return base;
-}
-
 template <int E>
 __device__ __forceinline__ uint64_t warp_select_compact(uint64_t* b, int k, int& kept, int grp = -1,
                                                         const int32_t* __restrict__ group_db = nullptr) {
@@ -431,18 +353,24 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
             __syncwarp();
         } else {
             const int k = p.k;
+            constexpr int EE = E > 0 ? E : 1;
+#pragma unroll 2
             for (int l = 0; l < 32; ++l) {
                 const int ql = __shfl_sync(0xffffffffu, q_row, l);
                 const bool vl = __shfl_sync(0xffffffffu, static_cast<int>(q_valid), l) != 0;
                 const uint64_t* from = p.part + (static_cast<size_t>(vl ? ql : 0) * p.n_slices + src) * k;
                 uint64_t* b = warp_buf + static_cast<size_t>(l) * C;
+                uint64_t key[EE];
+#pragma unroll
+                for (int e = 0; e < EE; ++e) {  // all loads of the list in flight at once: one round trip per list
+                    const int pos = e * 32 + static_cast<int>(lane);
+                    key[e] = (vl && pos < k) ? __ldcg(reinterpret_cast<const unsigned long long*>(from + pos)) : 0ull;
+                }
                 int n = 0;
 #pragma unroll
-                for (int e = 0; e < (E > 0 ? E : 1); ++e) {
-                    const int pos = e * 32 + static_cast<int>(lane);
-                    const uint64_t key = (vl && pos < k) ? __ldcg(reinterpret_cast<const unsigned long long*>(from + pos)) : 0ull;
-                    b[pos] = key;
-                    n += __popc(__ballot_sync(0xffffffffu, key != 0));
+                for (int e = 0; e < EE; ++e) {
+                    b[e * 32 + lane] = key[e];
+                    n += __popc(__ballot_sync(0xffffffffu, key[e] != 0));
                 }
                 if (static_cast<int>(lane) == l) st.cnt = n;
             }
@@ -591,7 +519,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         int it = 0;
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             if (p.wave_cnt != nullptr && it > 0) {
                 if (elect_one_sync()) wave_wait(p.wave_cnt + it - 1, wave_members(it - 1, n_items, gridDim.x, 1));
@@ -636,7 +564,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const int slice = w / p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -680,7 +608,7 @@ gemm_topk_ss_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * BLOCK_M + ewarp * 32 + lane) * C;
         for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             const int q_lanes = p.a_quarter > 0 ? p.a_quarter : 32;  // query rows owned by this warp
             const int q_base = qt * BLOCK_M + ewarp * q_lanes;
@@ -1019,6 +947,45 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 }
 
 // ===========================================================================
+// COLUMN DIRECTION (symmetric self-join).  When the queries are rows of the database itself, the score of
+// (query i, row j) is also the score of (query j, row i): a tile computed once can feed the top-k of its query
+// rows (the usual row-wise filter) AND the top-k of its database rows, with the query as the candidate.  The
+// column side keeps its state in global memory, one threshold / counter / key buffer per database row
+// (GemmTopkParams::col_*): thresholds are read once per tile (lane l holds the columns l, l+32, ...), a chunk of 32
+// columns is skipped when no score of the warp beats the smallest of its 32 thresholds, and a candidate claims
+// a slot with an atomicAdd on the row's counter.  Buffers are compacted between launches (col_compact_kernel):
+// a row that ran over its buffer is flagged and recomputed exactly by the caller.
+// ===========================================================================
+__device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], float m, float cthr_lane, float cmin, uint32_t row0,
+                                               uint32_t anchor, bool q_valid, const GemmTopkParams& p) {
+    if (!__any_sync(0xffffffffu, q_valid && m > cmin)) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float tj = __shfl_sync(0xffffffffu, cthr_lane, j);  // +inf for rows that do not collect
+        const float s = __uint_as_float(v[j]);
+        if (q_valid && s > tj) {
+            const uint32_t row = row0 + j;
+            if (row != anchor) {
+                const uint32_t pos = atomicAdd(p.col_cnt + row, 1u);
+                if (pos < static_cast<uint32_t>(p.col_cap))
+                    p.col_buf[static_cast<size_t>(row) * p.col_cap + pos] = make_key(s, anchor);
+            }
+        }
+    }
+}
+__device__ __forceinline__ float chunk_max32(const uint32_t (&v)[32]) {
+    float m4[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float m = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 3])), __uint_as_float(v[8 * g + 4]));
+        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 5])), __uint_as_float(v[8 * g + 6]));
+        m4[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+    }
+    return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
+// ===========================================================================
 // CTA pair (cta_group::2, M = 256) with the QUERIES RESIDENT ON CHIP.
 //
 //   * a cluster of two CTAs (one SM pair) owns 256 queries; each CTA keeps its
@@ -1038,7 +1005,7 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // K <= 768 (hybrid), <64, 12, 0, 12, 4> (all of K <= 768 in TMEM, N = 64).
 // L2 -> SM traffic per SM is a third of the streaming kernel's.
 // ===========================================================================
-template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES, int E>
+template <int BLOCK_N, int KB_T, int KB_S, int KB_STAGE, int STAGES, int E, bool COL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                      const __nv_bfloat16* __restrict__ q_pack, const int q_row_elems, const GemmTopkParams p) {
@@ -1109,7 +1076,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         int it = 0;
         for (int w = pair; w < n_items; w += n_pairs, ++it) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             if (p.wave_cnt != nullptr && it > 0) {
                 if (elect_one_sync()) wave_wait(p.wave_cnt + it - 1, wave_members(it - 1, n_items, n_pairs, 2));
@@ -1156,7 +1123,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             uint32_t acc_phase = 0, item_phase = 0;
             for (int w = pair; w < n_items; w += n_pairs) {
                 const int slice = w / p.q_tiles;
-                const int t0 = slice * p.tiles_per_slice;
+                const int t0 = p.tile0 + slice * p.tiles_per_slice;
                 const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
                 mbar_wait(a_ready, item_phase);  // both CTAs hold their query rows (TMEM + tail)
                 item_phase ^= 1;
@@ -1247,7 +1214,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32 + lane) * C;
         for (int w = pair; w < n_items; w += n_pairs) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             const int q_base = qt * 256 + static_cast<int>(rank) * 128 + ewarp * 32;
             const int q_row = q_base + lane;
@@ -1279,9 +1246,26 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C, qt, slice);
             if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
             for (int t = t0; t < t1; ++t) {
+                const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
+                // column direction: the thresholds of the tile's database rows, fetched while the MMA still runs
+                float cthr[COL ? BLOCK_N / 32 : 1], cmin[COL ? BLOCK_N / 32 : 1];
+                if constexpr (COL) {
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        const uint32_t r = row0 + c * 32 + lane;
+                        cthr[c] = (r >= static_cast<uint32_t>(p.col_row_min) && r < static_cast<uint32_t>(p.n_rows))
+                                      ? __ldcg(p.col_thr + r) : INFINITY;
+                    }
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        float mn = cthr[c];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                        cmin[c] = mn;
+                    }
+                }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
                 const uint32_t taddr = tmem_base + lane_base + A_COLS + acc * BLOCK_N;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 32) {
@@ -1297,6 +1281,14 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     }
                     if (!(dbg & 3))
                         scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room);
+                    if constexpr (COL) {
+                        float ct = cthr[0], cm = cmin[0];  // (the loop is not unrolled: pick the chunk's registers)
+#pragma unroll
+                        for (int q = 1; q < BLOCK_N / 32; ++q)
+                            if (c == q * 32) { ct = cthr[q]; cm = cmin[q]; }
+                        if (cm < INFINITY)  // warp-uniform: some row of the chunk collects
+                            scan_chunk_col(v, chunk_max32(v), ct, cm, row0 + c, self, q_valid, p);
+                    }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -1381,7 +1373,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         int it = 0;
         for (int w = pair; w < n_items; w += n_pairs, ++it) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             const int q_row0 = qt * 256 + static_cast<int>(rank) * 128;
             if (p.wave_cnt != nullptr && it > 0) {
@@ -1420,7 +1412,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             uint32_t acc_phase = 0;
             for (int w = pair; w < n_items; w += n_pairs) {
                 const int slice = w / p.q_tiles;
-                const int t0 = slice * p.tiles_per_slice;
+                const int t0 = p.tile0 + slice * p.tiles_per_slice;
                 const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -1464,7 +1456,7 @@ gemm_topk_ss2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32 + lane) * C;
         for (int w = pair; w < n_items; w += n_pairs) {
             const int slice = w / p.q_tiles, qt = w - slice * p.q_tiles;
-            const int t0 = slice * p.tiles_per_slice;
+            const int t0 = p.tile0 + slice * p.tiles_per_slice;
             const int t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
             const int q_base = qt * 256 + static_cast<int>(rank) * 128 + ewarp * 32;
             const int q_row = q_base + lane;

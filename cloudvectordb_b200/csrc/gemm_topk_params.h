@@ -30,6 +30,13 @@ struct GemmTopkParams {
     uint32_t* wave_cnt;  // [waves] producers that finished issuing the loads of their item in that wave (or null)
     uint32_t* done;      // [q_tiles][n_slices] epilogue warps that have flushed that item (zeroed; null: no inheritance)
     int done_full;       // warps that flush one item: 4 (single CTA) or 8 (CTA pair)
+    int tile0;       // first database tile of the launch (n_tiles stays the END tile; rows before tile0 are not scanned)
+    // column direction of a symmetric self-join (gemm_topk.cuh, scan_chunk_col); col_thr == null: off
+    const float* col_thr;  // [n_rows] a score must beat it to become a candidate of that database row
+    uint32_t* col_cnt;     // [n_rows] slots claimed in the row's buffer (may run past col_cap: the row overflowed)
+    uint64_t* col_buf;     // [n_rows][col_cap] keys (score, ~query id)
+    int col_cap;
+    int col_row_min;       // database rows below this do not collect
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
     int a_quarter;   // single-CTA kernel with one partial query tile: query rows per epilogue warp (the A tile is
                      // loaded as four 32-row boxes, box j = queries [j*a_quarter, j*a_quarter + 32)); 0 = one box

@@ -19,6 +19,9 @@ cudaError_t launch_ss2(int E, const CUtensorMap& tq, const CUtensorMap& tx, cons
 //      3 = K <= 768 all in TMEM with N=64 accumulators
 cudaError_t launch_ts2(int cfg, int E, const CUtensorMap& tx, const CUtensorMap& tq, const __nv_bfloat16* q_pack,
                        int q_row_elems, const GemmTopkParams& p, int grid, cudaStream_t st);
+// the same kernel with the column direction of the symmetric self-join (cfg 0 or 1, E in {1, 2, 4, 8})
+cudaError_t launch_ts2_col(int cfg, int E, const CUtensorMap& tx, const CUtensorMap& tq, const __nv_bfloat16* q_pack,
+                           int q_row_elems, const GemmTopkParams& p, int grid, cudaStream_t st);
 cudaError_t launch_grouped(int E, const CUtensorMap& tq, const CUtensorMap& tx, const GroupedParams& p, int grid,
                            cudaStream_t st);
 // transposed inverted-list scan (ivf_scan.cuh): list rows on the M side, <= 16 gathered queries per item, k <= 128

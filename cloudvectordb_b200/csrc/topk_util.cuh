@@ -97,6 +97,84 @@ __device__ __forceinline__ uint64_t warp_sorted_at(const uint64_t (&key)[E], int
         if ((pos >> 5) == e) sel = key[e];
     return shfl_u64(sel, pos & 31);
 }
+// The select itself, on keys held in registers (slot e*32+lane in key[e], 0 = empty): returns T such that the
+// survivors are exactly the non-empty keys >= T (the best k, or all of them when there are at most k), and sets
+// kth to a key whose score word is the k-th best score (0 when fewer than k candidates exist).
+template <int E>
+__device__ __forceinline__ uint64_t warp_select_threshold(const uint64_t (&key)[E], int k, uint64_t& kth) {
+    constexpr unsigned kFull = 0xffffffffu;
+    uint32_t hi[E];
+    int my_valid = 0;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        hi[e] = static_cast<uint32_t>(key[e] >> 32);  // 0 <=> empty slot (the score word of a real candidate is never 0)
+        my_valid += hi[e] != 0;
+        mx = max(mx, hi[e]);
+        mn = hi[e] != 0 ? min(mn, hi[e]) : mn;
+    }
+    const int n_valid = __reduce_add_sync(kFull, my_valid);
+    mx = __reduce_max_sync(kFull, mx);
+    mn = __reduce_min_sync(kFull, mn);
+    kth = 0;
+    if (n_valid <= k) {  // warp-uniform
+        if (n_valid == k) kth = (static_cast<uint64_t>(mn) << 32) | 1u;
+        return 1;  // keep every candidate
+    }
+    uint32_t prefix = mx;
+    const uint32_t diff = mx ^ mn;
+    if (diff != 0) {
+        int bit = 31 - __clz(diff);
+        prefix = mx & ~((2u << bit) - 1u);  // the bits every candidate shares
+        for (; bit >= 0; --bit) {
+            const uint32_t trial = prefix | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) c += hi[e] >= trial;
+            if (__reduce_add_sync(kFull, c) >= k) prefix = trial;
+        }
+    }
+    // prefix == the k-th largest score word
+    int c_gt = 0, c_eq = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        c_gt += hi[e] > prefix;
+        c_eq += hi[e] == prefix;
+    }
+    c_gt = __reduce_add_sync(kFull, c_gt);
+    c_eq = __reduce_add_sync(kFull, c_eq);
+    const int need = k - c_gt;  // how many of the rows tied at the k-th score stay: the lowest ids
+    uint32_t low = 0;
+    if (need < c_eq) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = low | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) c += (hi[e] == prefix) && (static_cast<uint32_t>(key[e]) >= trial);
+            if (__reduce_add_sync(kFull, c) >= need) low = trial;
+        }
+    }
+    const uint64_t T = (static_cast<uint64_t>(prefix) << 32) | low;
+    kth = T | 1u;
+    return T;
+}
+
+// Move the survivors (non-empty keys >= T) to the front of `b`, in any order; returns how many there are.
+template <int E>
+__device__ __forceinline__ int warp_store_survivors(uint64_t* b, const uint64_t (&key)[E], uint64_t T) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const bool keep = (key[e] >> 32) != 0 && key[e] >= T;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) b[base + __popc(m & lt_mask)] = key[e];
+        base += __popc(m);
+    }
+    return base;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace cvdb

@@ -19,7 +19,7 @@ except Exception:  # pragma: no cover
 
 def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, metric: str = "ip",
                         storage: str = "bf16", device: int = 0, chunk: int = 65536, index=None,
-                        row_offset: int = 0, queries=None, query_groups=None):
+                        row_offset: int = 0, queries=None, query_groups=None, symmetric: bool = False):
     """Top-k most similar rows of `emb` for every row (or for `queries`), never
     returning the anchor row itself nor any row with the anchor's group id.
 
@@ -36,6 +36,18 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
         index.add(emb)
         if groups is not None:
             index.set_groups(groups)
+    if symmetric:
+        # every tile of X.X^T once, selected in both directions (half the flops); whole-matrix self-join only
+        if queries is not None or not exclude_self or metric.lower() != "ip" or storage.lower() != "bf16" or row_offset:
+            raise ValueError("symmetric=True is the plain self-join: IP metric, bf16 storage, all rows as anchors")
+        D, I = mine_hard_negatives_symmetric(index, k, emb=emb, groups=groups, chunk=chunk)
+        if own:
+            index.close()
+        if _is_torch(emb) and emb.is_cuda:
+            return D, I
+        if _is_torch(emb):
+            return D.cpu(), I.cpu()
+        return D.cpu().numpy(), I.cpu().numpy()
     if queries is None:
         queries, query_groups = emb, groups
     m = int(queries.shape[0])
@@ -52,6 +64,66 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
     if _is_torch(outs_d[0]):
         return torch.cat(outs_d), torch.cat(outs_i)
     return np.concatenate(outs_d), np.concatenate(outs_i)
+
+
+def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 256):
+    """Anchor chunks of the symmetric self-join: (row0, rows) in row order, sizes 256, 256, 512, 1024, ... (each at
+    most the number of rows before it, so a row's column buffer sees about k new candidates per chunk) up to `chunk`."""
+    out, r = [], 0
+    while r < n:
+        m = min(first if r == 0 else min(chunk, r), n - r)
+        out.append((r, m))
+        r += m
+    return out
+
+
+def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=None, chunk: int = 65536,
+                                  first_chunk: int = 256, stats: Optional[dict] = None):
+    """Self-join top-k over ALL rows of `index` (IP, bf16 storage, groups already set with set_groups) that computes
+    every tile of X.X^T once and selects in both directions (include/cvdb_b200.h, cvdb_selfjoin_*): half the flops
+    of mine_hard_negatives().  Rows whose column buffer overflowed (adversarial row orders) are recomputed exactly
+    with a plain search; that needs `emb` (and `groups`).  Returns (D [n, k] f32, I [n, k] i64) on the GPU."""
+    lib = _C.lib()
+    n = index.ntotal
+    dev = torch.device("cuda", index.device)
+    stream = int(torch.cuda.current_stream(index.device).cuda_stream)
+    if chunk % 256 or first_chunk % 256:
+        raise ValueError("chunk sizes must be multiples of 256")
+    _C.check(lib.cvdb_selfjoin_begin(index._h, int(k), stream))
+    try:
+        keys = torch.empty((n, k), dtype=torch.int64, device=dev)
+        sched = selfjoin_schedule(n, chunk, first_chunk)
+        for r0, m in sched:
+            _C.check(lib.cvdb_selfjoin_chunk(index._h, r0, m, keys[r0:].data_ptr(), stream))
+        D = torch.empty((n, k), dtype=torch.float32, device=dev)
+        I = torch.empty((n, k), dtype=torch.int64, device=dev)
+        _C.check(lib.cvdb_selfjoin_finish(index._h, 0, n, keys.data_ptr(), D.data_ptr(), I.data_ptr(), stream))
+        del keys
+        max_dirty = min(n, 1 << 22)
+        rows = torch.empty((max_dirty,), dtype=torch.int32, device=dev)
+        nd = _C.C.c_int64(0)
+        _C.check(lib.cvdb_selfjoin_dirty(index._h, rows.data_ptr(), max_dirty, _C.C.byref(nd), stream))
+    finally:
+        _C.check(lib.cvdb_selfjoin_end(index._h))
+    n_dirty = int(nd.value)
+    if stats is not None:
+        stats.update(chunks=len(sched), dirty_rows=n_dirty)
+    if n_dirty:
+        # exact recomputation of the rows that lost column candidates (plain row-direction search of the whole index)
+        if emb is None:
+            raise RuntimeError(f"{n_dirty} rows overflowed their column buffer and no `emb` was given to recompute them")
+        if n_dirty > max_dirty:
+            rows = torch.arange(n, device=dev, dtype=torch.int32)        # hopeless order: everything the plain way
+        else:
+            rows = rows[:n_dirty].sort().values
+        emb_t = emb if _is_torch(emb) else torch.from_numpy(np.ascontiguousarray(emb))
+        g_t = None if groups is None else torch.as_tensor(groups).to(dev).to(torch.int32)
+        for q0 in range(0, rows.numel(), 65536):
+            rr = rows[q0:q0 + 65536].long()
+            q = emb_t[rr.to(emb_t.device)].to(dev)
+            Dq, Iq = index.search(q, k, self_ids=rr.to(torch.int32), group_q=None if g_t is None else g_t[rr])
+            D[rr], I[rr] = Dq, Iq
+    return D, I
 
 
 def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, exclude_self: bool = True,

@@ -178,6 +178,31 @@ int cvdb_index_search_keys(cvdb_index_t idx, const void* q, int64_t nq, int dtyp
 int cvdb_index_merge_keys(cvdb_index_t idx, const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, float* D,
                           int64_t* I, void* stream);
 
+/* -- symmetric self-join (hard-negative mining over the index's OWN rows; README.md:2 "dataset of triplets") -----
+ * A self-join computes every score twice: (anchor i, row j) and (anchor j, row i).  These calls compute each tile of
+ * X.X^T once and select in both directions: the anchors of a chunk get their top-k among the rows AT OR AFTER the chunk
+ * (row direction, the usual fused epilogue), and every row AFTER the chunk is offered the chunk's anchors as candidates
+ * (column direction: per-row threshold / counter / 256-key buffer in HBM, compacted after every chunk).  Walking the
+ * chunks in row order covers every ordered pair exactly once with half the flops of the plain join.
+ * IP metric, bf16 storage, padded d <= 768, 2 <= k <= 124; self and same-group rows (cvdb_index_set_groups) are
+ * excluded in both directions.  2 KB of HBM per index row while the join is open.  All pointers are DEVICE pointers.
+ *   begin   opens a join for the current rows of the index
+ *   chunk   anchors = rows [row0, row0 + nrows), row0 a multiple of 128, nrows <= 65536, chunks in increasing row order
+ *           and contiguous; writes the row-direction result of the chunk as keys [nrows][k] (see cvdb_index_search_keys).
+ *           Chunk sizes should start small and at most double (256, 256, 512, 1024, ...): a row's buffer takes the
+ *           candidates of ONE chunk under the threshold of the chunks before it
+ *   finish  merges the row-direction keys of rows [row0, row0 + nrows) with their column lists -> D, I (any row range,
+ *           after the last chunk)
+ *   dirty   rows whose column buffer overflowed (their lists lost candidates): writes up to max_out row ids, returns
+ *           the count; the caller recomputes those rows with cvdb_index_search (exact, with the same exclusion)
+ *   end     frees the join state */
+int cvdb_selfjoin_begin(cvdb_index_t idx, int k, void* stream);
+int cvdb_selfjoin_chunk(cvdb_index_t idx, int64_t row0, int64_t nrows, uint64_t* keys, void* stream);
+int cvdb_selfjoin_finish(cvdb_index_t idx, int64_t row0, int64_t nrows, const uint64_t* row_keys, float* D, int64_t* I,
+                         void* stream);
+int cvdb_selfjoin_dirty(cvdb_index_t idx, int32_t* rows_out, int64_t max_out, int64_t* n_out, void* stream);
+int cvdb_selfjoin_end(cvdb_index_t idx);
+
 /* -- k-means update (IVF coarse quantizer) --------------------------------
  * sums [K,d] f32 += x[i] for assign[i]; counts [K] i32 += 1.  The caller zeroes
  * sums/counts and all-reduces them across ranks.  Device pointers only. */

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--ks", default="10,50,100,200")
     ap.add_argument("--mine-ks", default="50,100")
     ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--flags", default="0", help="comma list of debug_flags to A/B in-process (128 = no slice inheritance)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "k_sweep.jsonl"))
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -56,11 +57,13 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters, float(np.median(idx.profile_ms())), out
 
+    flags = [int(v) for v in a.flags.split(",")]
     for k in [int(v) for v in a.ks.split(",")]:
-        ms, kms, _ = run(lambda: idx.search(xq, k, profile=True))
-        w = idx.last_work()
-        emit(shape=f"{a.rows}x{d}, {nq} queries", k=k, ms=ms, kernel_ms=kms, qps=nq / ms * 1e3,
-             tflops=w["flops"] / kms / 1e9, variant=w["variant"], n_slices=w["n_slices"])
+        for fl in flags:
+            ms, kms, _ = run(lambda: idx.search(xq, k, profile=True, debug_flags=fl))
+            w = idx.last_work()
+            emit(shape=f"{a.rows}x{d}, {nq} queries", k=k, debug_flags=fl, ms=ms, kernel_ms=kms, qps=nq / ms * 1e3,
+                 tflops=w["flops"] / kms / 1e9, variant=w["variant"], n_slices=w["n_slices"])
     rows_m = min(a.rows, 6_250_000)
     idx.truncate(rows_m)
     groups = (torch.arange(rows_m, device=dev) // 4).to(torch.int32)
@@ -69,10 +72,11 @@ def main():
     self_ids = torch.arange(65536, device=dev, dtype=torch.int32)
     gq = groups[:65536]
     for k in [int(v) for v in a.mine_ks.split(",")]:
-        ms, kms, _ = run(lambda: idx.search(anchors, k, self_ids=self_ids, group_q=gq, profile=True), iters=3)
-        w = idx.last_work()
-        emit(shape=f"mining chunk {rows_m}x{d}, 65536 anchors, self+group exclusion", k=k, ms=ms, kernel_ms=kms,
-             tflops=w["flops"] / kms / 1e9, variant=w["variant"], n_slices=w["n_slices"])
+        for fl in flags + flags:     # twice, interleaved: shows the run-to-run spread next to the A/B difference
+            ms, kms, _ = run(lambda: idx.search(anchors, k, self_ids=self_ids, group_q=gq, profile=True, debug_flags=fl), iters=3)
+            w = idx.last_work()
+            emit(shape=f"mining chunk {rows_m}x{d}, 65536 anchors, self+group exclusion", k=k, debug_flags=fl, ms=ms,
+                 kernel_ms=kms, tflops=w["flops"] / kms / 1e9, variant=w["variant"], n_slices=w["n_slices"])
     idx.close()
 
 
