@@ -11,8 +11,8 @@ from .index import IndexFlat, IndexFlatIP, IndexFlatL2, merge_topk  # noqa: F401
 from .ivf import IndexIVFFlat  # noqa: F401
 from .kmeans import Kmeans  # noqa: F401
 from .mining import (build_triplets, mine_hard_negatives, mine_hard_negatives_sharded,  # noqa: F401
-                     mine_hard_negatives_symmetric, selfjoin_schedule)
+                     mine_hard_negatives_sharded_symmetric, mine_hard_negatives_symmetric, selfjoin_schedule)
 from .sharded import ShardedIndex, ShardedIVFFlat  # noqa: F401
 
 __all__ = ["IndexIVFFlat", "IndexFlat", "IndexFlatIP", "IndexFlatL2", "merge_topk", "Kmeans", "build_triplets", "mine_hard_negatives",
-           "mine_hard_negatives_sharded", "mine_hard_negatives_symmetric", "selfjoin_schedule", "ShardedIndex", "ShardedIVFFlat"]
+           "mine_hard_negatives_sharded", "mine_hard_negatives_sharded_symmetric", "mine_hard_negatives_symmetric", "selfjoin_schedule", "ShardedIndex", "ShardedIVFFlat"]

@@ -517,16 +517,15 @@ __global__ void build_triplets_kernel(const int64_t* __restrict__ I, const float
 // ---------------------------------------------------------------------------
 // Symmetric self-join, column direction (gemm_topk.cuh, scan_chunk_col): per database row a buffer of
 // kColCap keys, the first col_base[r] of which are the survivors of the previous compaction.
-// col_compact: one warp per row that received candidates since then: drop same-group candidates, keep the best
-// k (select, not sort), publish the row's new threshold.  A row whose counter ran past the buffer lost
+// col_compact: one warp per row that received candidates since then: keep the best k (select, not sort), publish
+// the row's new threshold (same-group candidates were refused when they were offered).  A row whose counter ran past the buffer lost
 // candidates: it is flagged dirty (the caller recomputes it exactly) and stops collecting.
 // ---------------------------------------------------------------------------
 constexpr int kColCap = 256;
 
 __global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __restrict__ col_cnt,
                                    uint32_t* __restrict__ col_base, float* __restrict__ col_thr,
-                                   uint8_t* __restrict__ dirty, int k, int64_t row_min, int64_t n_rows,
-                                   const int32_t* __restrict__ group_db) {
+                                   uint8_t* __restrict__ dirty, int k, int64_t row_min, int64_t n_rows) {
     constexpr int E = kColCap / 32;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -548,14 +547,6 @@ __global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __r
         for (int e = 0; e < E; ++e) {
             const uint32_t pos = e * 32 + lane;
             key[e] = pos < cnt ? b[pos] : 0;
-        }
-        if (group_db != nullptr) {
-            const int grp = group_db[r];
-            if (grp >= 0) {
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (key[e] != 0 && group_db[key_row(key[e])] == grp) key[e] = 0;
-            }
         }
         uint64_t kth;
         const uint64_t T = warp_select_threshold<E>(key, k, kth);

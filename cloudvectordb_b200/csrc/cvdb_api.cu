@@ -502,8 +502,10 @@ struct SearchExtra {
     const __nv_bfloat16* q_packed = nullptr;  // packed query rows (nq of them used)
     int64_t q_rows_avail = 0;                 // rows readable from q_packed on
     int64_t row_begin = 0;                    // first database row scanned (multiple of 128)
+    int64_t row_end = 0;                      // database rows scanned end here (0: ntotal)
     bool col = false;                         // column direction on (Index::col_*)
     int64_t col_row_min = 0;                  // database rows below this do not collect
+    const int32_t* q_ids = nullptr;           // [nq] ids the column lists record for the queries (null: self_ids)
 };
 
 // `keys_out` (optional, instead of D/I): the merged top-k as keys carrying the caller's ids (shard exchange).
@@ -544,8 +546,9 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     }
 
     GemmTopkParams p{};
+    const int64_t scan_end = (ex && ex->row_end > 0) ? std::min<int64_t>(ex->row_end, ix->ntotal) : ix->ntotal;
     p.nq = static_cast<int>(nq);
-    p.n_rows = static_cast<int>(ix->ntotal);
+    p.n_rows = static_cast<int>(scan_end);
     p.k = k;
     p.room = compaction_trigger(k, C);
     p.dbg = opts ? opts->debug_flags : 0;
@@ -600,7 +603,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     const int sms = ix->num_sms;
     const int workers = variant == 1 ? sms : sms / 2;  // CTAs or CTA pairs
     p.q_tiles = static_cast<int>(ceil_div(nq, q_tile));
-    p.n_tiles = static_cast<int>(ceil_div(ix->ntotal, block_n));  // END tile of the scan
+    p.n_tiles = static_cast<int>(ceil_div(scan_end, block_n));  // END tile of the scan
     p.tile0 = ex ? static_cast<int>(ex->row_begin / block_n) : 0;
     const int scan_tiles = p.n_tiles - p.tile0;
     // keep the per-slice result scratch under ~1 GiB
@@ -633,9 +636,10 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq + n_waves + n_items) * 4, st));
         p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
         p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->gthr.as<uint32_t>() + nq;
-        // a slice starts from the result of the latest finished earlier slice of its query tile (gemm_topk.cuh,
-        // item_begin): worth a few microseconds per item once slices are long and k > 1
-        const bool inherit = E > 0 && E <= 16 && p.n_slices > 1 && p.tiles_per_slice >= 32 && !(opts && (opts->debug_flags & 128));
+        // Optional (debug flag 128): a slice starts from the result of the latest finished earlier slice of its query
+        // tile (gemm_topk.cuh, item_begin).  Exact either way.  Same-box A/B (profiles/r2_inheritance_ab.jsonl): +1 % at
+        // k = 50 on the headline shape, but -4 % on the mining chunk and -21 % at k = 200, so it is off by default.
+        const bool inherit = E > 0 && E <= 16 && p.n_slices > 1 && p.tiles_per_slice >= 32 && opts && (opts->debug_flags & 128);
         p.done = inherit ? ix->gthr.as<uint32_t>() + nq + n_waves : nullptr;
         p.done_full = variant == 1 ? 4 : 8;
     }
@@ -666,6 +670,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
             p.col_buf = ix->col_buf.as<uint64_t>();
             p.col_cap = kColCap;
             p.col_row_min = static_cast<int>(ex->col_row_min);
+            p.q_ids = ex->q_ids;
             LAUNCH(launch_ts2_col(cfg, E, tx, tq, q_rows, ix->row_elems, p, grid, st));
         } else {
             LAUNCH(launch_ts2(cfg, E, tx, tq, q_rows, ix->row_elems, p, grid, st));
@@ -680,7 +685,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         ix->prof_head = (slot + 1) % Index::kProfSlots;
         ix->prof_count = std::min(ix->prof_count + 1, Index::kProfSlots);
     }
-    const double rows_scanned = double(ix->ntotal) - (ex ? double(ex->row_begin) : 0.0);
+    const double rows_scanned = double(scan_end) - (ex ? double(ex->row_begin) : 0.0);
     ix->last_flops = 2.0 * double(nq) * rows_scanned * double(ix->d);
     ix->last_bytes = rows_scanned * double(ix->row_elems) * 2.0;
     ix->last_slices = p.n_slices;
@@ -1404,40 +1409,81 @@ int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
     return CVDB_OK;
 }
 
-int cvdb_selfjoin_chunk(cvdb_index_t h, int64_t row0, int64_t nrows, uint64_t* keys, void* stream) {
+namespace {
+int selfjoin_compact(Index* ix, int64_t row_min, int64_t row_end, cudaStream_t st) {
+    if (row_min >= row_end) return CVDB_OK;
+    const int64_t blocks = std::min<int64_t>(ceil_div(row_end - row_min, 8), 148 * 32);
+    col_compact_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
+                                                                      ix->col_base.as<uint32_t>(), ix->col_thr.as<float>(),
+                                                                      ix->col_dirty.as<uint8_t>(), ix->sj_k, row_min, row_end);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return CVDB_OK;
+}
+}  // namespace
+
+int cvdb_selfjoin_chunk(cvdb_index_t h, int64_t row0, int64_t nrows, int64_t id_base, uint64_t* keys, void* stream) {
     TRY(check_index(h));
     Index* ix = reinterpret_cast<Index*>(h);
     if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
     if (row0 < 0 || nrows < 1 || row0 + nrows > ix->ntotal) return fail(CVDB_EINVAL, "anchor rows outside the index");
     if (row0 % 128) return fail(CVDB_EINVAL, "row0 must be a multiple of 128 (the scan starts at a tile boundary)");
     if (nrows > 65536) return fail(CVDB_ELIMIT, "at most 65536 anchors per chunk");
+    if (id_base < 0 || id_base + ix->ntotal > 0xFFFFFFFELL) return fail(CVDB_ELIMIT, "ids must stay below 2^32 - 1");
     if (!keys) return fail(CVDB_EINVAL, "null pointer");
     cvdb_guard g(ix->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     StreamOrder order(ix, st);
     const int k = ix->sj_k;
     TRY(ix->ids_a.ensure(static_cast<size_t>(nrows) * 4));
-    iota_kernel<<<static_cast<unsigned>(ceil_div(nrows, 256)), 256, 0, st>>>(ix->ids_a.as<int32_t>(), row0, nrows);
-    ++g_launches;
+    TRY(ix->ids_b.ensure(static_cast<size_t>(nrows) * 4));
+    const unsigned ib = static_cast<unsigned>(ceil_div(nrows, 256));
+    iota_kernel<<<ib, 256, 0, st>>>(ix->ids_a.as<int32_t>(), row0, nrows);            // the row that IS the anchor
+    iota_kernel<<<ib, 256, 0, st>>>(ix->ids_b.as<int32_t>(), row0 + id_base, nrows);  // its id in the column lists
+    g_launches += 2;
     SearchExtra ex;
     ex.q_packed = ix->x + row0 * ix->row_elems;
     ex.q_rows_avail = ix->ntotal - row0;
     ex.row_begin = row0;
     ex.col = true;
     ex.col_row_min = row0 + nrows;
+    ex.q_ids = ix->ids_b.as<int32_t>();
     const int32_t* grp = ix->has_groups ? ix->groups.as<int32_t>() + row0 : nullptr;
-    TRY(search_device(ix, nullptr, nrows, CVDB_DTYPE_BF16, k, nullptr, nullptr, nullptr, ix->ids_a.as<int32_t>(), grp, nullptr, st,
+    cvdb_search_opts o{};
+    o.id_base = id_base;
+    TRY(search_device(ix, nullptr, nrows, CVDB_DTYPE_BF16, k, nullptr, nullptr, nullptr, ix->ids_a.as<int32_t>(), grp, &o, st,
                       keys, nullptr, &ex));
-    if (row0 + nrows < ix->ntotal) {
-        const int64_t m = ix->ntotal - (row0 + nrows);
-        const int64_t blocks = std::min<int64_t>(ceil_div(m, 8), 148 * 32);
-        col_compact_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-            ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(), ix->col_base.as<uint32_t>(), ix->col_thr.as<float>(),
-            ix->col_dirty.as<uint8_t>(), k, row0 + nrows, ix->ntotal, ix->has_groups ? ix->groups.as<int32_t>() : nullptr);
-        ++g_launches;
-        CU_TRY(cudaGetLastError());
-    }
-    return CVDB_OK;
+    return selfjoin_compact(ix, row0 + nrows, ix->ntotal, st);
+}
+
+int cvdb_selfjoin_cross(cvdb_index_t h, const void* q, int64_t nq, int dtype, const int32_t* q_ids, const int32_t* group_q,
+                        int64_t row_begin, int64_t row_end, int64_t id_base, uint64_t* keys, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
+    if (nq < 1 || nq > 65536) return fail(CVDB_ELIMIT, "1..65536 anchors per call");
+    if (dtype != CVDB_DTYPE_F32 && dtype != CVDB_DTYPE_BF16 && dtype != CVDB_DTYPE_F16)
+        return fail(CVDB_EINVAL, "unknown dtype %d", dtype);
+    if (row_end <= 0) row_end = ix->ntotal;
+    if (row_begin < 0 || row_begin % 128 || row_begin >= row_end || row_end > ix->ntotal)
+        return fail(CVDB_EINVAL, "row range [%lld, %lld) must start at a multiple of 128 inside the index",
+                    static_cast<long long>(row_begin), static_cast<long long>(row_end));
+    if (id_base < 0 || id_base + ix->ntotal > 0xFFFFFFFELL) return fail(CVDB_ELIMIT, "ids must stay below 2^32 - 1");
+    if (!q || !q_ids || !keys) return fail(CVDB_EINVAL, "null pointer");
+    if (group_q && !ix->has_groups) return fail(CVDB_EINVAL, "group_q given but the index has no groups");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    SearchExtra ex;
+    ex.row_begin = row_begin;
+    ex.row_end = row_end;
+    ex.col = true;
+    ex.col_row_min = row_begin;
+    ex.q_ids = q_ids;
+    cvdb_search_opts o{};
+    o.id_base = id_base;
+    TRY(search_device(ix, q, nq, dtype, ix->sj_k, nullptr, nullptr, nullptr, nullptr, group_q, &o, st, keys, nullptr, &ex));
+    return selfjoin_compact(ix, row_begin, row_end, st);
 }
 
 int cvdb_selfjoin_finish(cvdb_index_t h, int64_t row0, int64_t nrows, const uint64_t* row_keys, float* D, int64_t* I,
@@ -1520,6 +1566,15 @@ int cvdb_index_search_keys(cvdb_index_t h, const void* q, int64_t nq, int dtype,
                           ix->q_norm.as<float>() + q0));
     }
     return CVDB_OK;
+}
+
+int cvdb_merge_keys(const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, uint64_t* keys_out, void* stream) {
+    if (nq < 0 || nlists < 1 || k_in < 1 || k < 1 || k > CVDB_MAX_K) return fail(CVDB_EINVAL, "bad sizes");
+    if (nq == 0) return CVDB_OK;
+    if (!keys || !keys_out) return fail(CVDB_EINVAL, "null pointer");
+    ptr_guard g(keys);
+    return launch_merge(keys, nq, nlists, k_in, k, 0, nullptr, 0, k_in, static_cast<int64_t>(nq) * k_in, nullptr, 0, nullptr,
+                        nullptr, nullptr, keys_out, static_cast<cudaStream_t>(stream));
 }
 
 int cvdb_index_merge_keys(cvdb_index_t h, const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, float* D,

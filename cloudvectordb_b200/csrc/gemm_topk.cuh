@@ -322,7 +322,8 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 
 // Start of a work item: reset the selection state of this thread's query.
 //
-// INHERITANCE.  A slice that starts from an empty buffer only ever learns the k-th best score of ITS OWN rows,
+// INHERITANCE (optional, p.done != null; off by default: see cvdb_api.cu for the A/B that decided it).
+// A slice that starts from an empty buffer only ever learns the k-th best score of ITS OWN rows,
 // and the shared threshold gthr[q] is the best such single-slice value: with S slices every slice still collects
 // about k candidates per query, S*k in all, where a scan of the whole database with one running threshold would
 // collect ~k*ln(N/k).  At k = 200 on the headline shape that made every second 32x32 chunk take the slow
@@ -956,8 +957,13 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // a slot with an atomicAdd on the row's counter.  Buffers are compacted between launches (col_compact_kernel):
 // a row that ran over its buffer is flagged and recomputed exactly by the caller.
 // ===========================================================================
+// anchor_id: the query's id in the id space of the column lists (a global id when the database is one shard of
+// many); self_row: the database row that IS the query (none: 0xFFFFFFFF); grp: the query's group (< 0: none) -- a
+// row of the same group is not offered the query (checked here, per candidate: the claim of a slot is a global
+// round trip anyway).
 __device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], float m, float cthr_lane, float cmin, uint32_t row0,
-                                               uint32_t anchor, bool q_valid, const GemmTopkParams& p) {
+                                               uint32_t anchor_id, uint32_t self_row, int grp, bool q_valid,
+                                               const GemmTopkParams& p) {
     if (!__any_sync(0xffffffffu, q_valid && m > cmin)) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -965,10 +971,10 @@ __device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], float m,
         const float s = __uint_as_float(v[j]);
         if (q_valid && s > tj) {
             const uint32_t row = row0 + j;
-            if (row != anchor) {
+            if (row != self_row && !(grp >= 0 && p.group_db != nullptr && __ldg(p.group_db + row) == grp)) {
                 const uint32_t pos = atomicAdd(p.col_cnt + row, 1u);
                 if (pos < static_cast<uint32_t>(p.col_cap))
-                    p.col_buf[static_cast<size_t>(row) * p.col_cap + pos] = make_key(s, anchor);
+                    p.col_buf[static_cast<size_t>(row) * p.col_cap + pos] = make_key(s, anchor_id);
             }
         }
     }
@@ -1245,6 +1251,10 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const int grp = (p.group_q && q_valid) ? __ldg(p.group_q + q_row) : -1;
             item_begin<E>(st, p, q_row, q_valid, p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32) * C, qt, slice);
             if constexpr (E > 0) st.grp = p.group_db != nullptr ? grp : -1;
+            uint32_t anchor_id = self;
+            if constexpr (COL) {
+                if (p.q_ids != nullptr && q_valid) anchor_id = static_cast<uint32_t>(__ldg(p.q_ids + q_row));
+            }
             for (int t = t0; t < t1; ++t) {
                 const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
                 // column direction: the thresholds of the tile's database rows, fetched while the MMA still runs
@@ -1287,7 +1297,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         for (int q = 1; q < BLOCK_N / 32; ++q)
                             if (c == q * 32) { ct = cthr[q]; cm = cmin[q]; }
                         if (cm < INFINITY)  // warp-uniform: some row of the chunk collects
-                            scan_chunk_col(v, chunk_max32(v), ct, cm, row0 + c, self, q_valid, p);
+                            scan_chunk_col(v, chunk_max32(v), ct, cm, row0 + c, anchor_id, self, grp, q_valid, p);
                     }
                 }
                 acc ^= 1;

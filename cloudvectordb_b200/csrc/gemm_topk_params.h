@@ -37,6 +37,7 @@ struct GemmTopkParams {
     uint64_t* col_buf;     // [n_rows][col_cap] keys (score, ~query id)
     int col_cap;
     int col_row_min;       // database rows below this do not collect
+    const int32_t* q_ids;  // [nq] id of query i in the id space of the column lists (null: self_ids[i])
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
     int a_quarter;   // single-CTA kernel with one partial query tile: query rows per epilogue warp (the A tile is
                      // loaded as four 32-row boxes, box j = queries [j*a_quarter, j*a_quarter + 32)); 0 = one box

@@ -94,7 +94,7 @@ def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=
         keys = torch.empty((n, k), dtype=torch.int64, device=dev)
         sched = selfjoin_schedule(n, chunk, first_chunk)
         for r0, m in sched:
-            _C.check(lib.cvdb_selfjoin_chunk(index._h, r0, m, keys[r0:].data_ptr(), stream))
+            _C.check(lib.cvdb_selfjoin_chunk(index._h, r0, m, 0, keys[r0:].data_ptr(), stream))
         D = torch.empty((n, k), dtype=torch.float32, device=dev)
         I = torch.empty((n, k), dtype=torch.int64, device=dev)
         _C.check(lib.cvdb_selfjoin_finish(index._h, 0, n, keys.data_ptr(), D.data_ptr(), I.data_ptr(), stream))
@@ -166,6 +166,140 @@ def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, 
     if not outs_d:
         return (torch.empty((0, k), dtype=torch.float32, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
     return torch.cat(outs_d), torch.cat(outs_i)
+
+
+def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups=None, *, chunk: int = 65536,
+                                          first_chunk: int = 256, stats: Optional[dict] = None):
+    """The symmetric self-join over a ShardedIndex (one process per GPU, NCCL): every unordered pair of rows is
+    scored once in the whole job.
+
+    Shard pairs.  The block (anchors of shard h) x (rows of shard g) and its transpose hold the same scores, so only
+    ONE of the two ranks computes it -- in both directions at once (cvdb_selfjoin_cross): the row direction gives
+    the anchors of h their candidates among g's rows (sent back to h), the column direction gives g's rows their
+    candidates among h's anchors (kept in g's column lists).  Rank g takes the anchors of the owners at distance
+    1 .. (G-1)/2 after it (mod G); with an even number of ranks the pair at distance G/2 is split by rows: the lower
+    rank computes (all anchors of the upper) x (its first half), the upper rank (second-half anchors of the lower) x
+    (all its rows).  The diagonal block is the single-GPU symmetric join (cvdb_selfjoin_chunk).  Every rank does
+    (G/2)/G of the plain job's flops.
+
+    Steps.  All owners walk the same doubling chunk schedule (selfjoin_schedule); step s: all-gather chunk s of every
+    owner (vectors, groups), each rank runs its 1 + (G-1)/2 (+1/2) blocks, the row-direction keys go to the
+    anchors' owners with ONE all_to_all, and the owner merges the G lists into its running row keys.  After the last
+    step cvdb_selfjoin_finish merges row keys and column lists.  Rows whose column buffer overflowed anywhere are
+    recomputed by the plain sharded search (collectively).
+
+    Returns (D [n_local, k] f32, I [n_local, k] i64 global ids) for this rank's rows, on the GPU."""
+    import torch.distributed as dist
+    lib = _C.lib()
+    G, g = index.world, index.rank
+    local = index.local
+    dev = local_emb.device
+    counts = list(index._counts)
+    bases = [sum(counts[:h]) for h in range(G)]
+    n_loc, d = counts[g], int(local_emb.shape[1])
+    stream = int(torch.cuda.current_stream(dev.index).cuda_stream)
+    sched = [selfjoin_schedule(c, chunk, first_chunk) for c in counts]
+    steps = max(len(sc) for sc in sched)
+    # the chunk boundary nearest to the middle of every shard (the row split of the distance-G/2 pairs)
+    half_idx = [min(range(len(sc)), key=lambda i: abs(sc[i][0] - c // 2)) if sc else 0 for sc, c in zip(sched, counts)]
+    half_row = [sc[i][0] if sc else 0 for sc, i in zip(sched, half_idx)]
+    full_d = (G - 1) // 2
+    has_groups = local_groups is not None
+    grp_dev = local_groups.to(dev).to(torch.int32).contiguous() if has_groups else None
+    _C.check(lib.cvdb_selfjoin_begin(local._h, int(k), stream))
+    n_blocks = 0
+    try:
+        row_keys = torch.zeros((n_loc, k), dtype=torch.int64, device=dev)
+        for s_i in range(steps):
+            ch = [sc[s_i] if s_i < len(sc) else (0, 0) for sc in sched]
+            m_max = max(m for _, m in ch)
+            r0, m = ch[g]
+            q_mine = torch.zeros((m_max, d), dtype=local_emb.dtype, device=dev)
+            g_mine = torch.full((m_max,), -1, dtype=torch.int32, device=dev)
+            if m:
+                q_mine[:m] = local_emb[r0:r0 + m]
+                if has_groups:
+                    g_mine[:m] = grp_dev[r0:r0 + m]
+            Q = torch.empty((G, m_max, d), dtype=local_emb.dtype, device=dev)
+            GR = torch.empty((G, m_max), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(Q.view(G * m_max, d), q_mine, group=index.group)
+            dist.all_gather_into_tensor(GR.view(-1), g_mine, group=index.group)
+            send = torch.zeros((G, m_max, k), dtype=torch.int64, device=dev)
+            if m:   # the diagonal block
+                _C.check(lib.cvdb_selfjoin_chunk(local._h, r0, m, bases[g], send[g].data_ptr(), stream))
+                n_blocks += 1
+
+            def cross(h, row_begin, row_end):
+                hr0, hm = ch[h]
+                if hm == 0 or n_loc == 0:
+                    return 0
+                ids = (torch.arange(hm, device=dev, dtype=torch.int64) + (bases[h] + hr0)).to(torch.int32)
+                dt = {torch.float32: _C.DTYPE_F32, torch.bfloat16: _C.DTYPE_BF16, torch.float16: _C.DTYPE_F16}[Q.dtype]
+                qh = Q[h, :hm].contiguous()
+                gh = GR[h, :hm].contiguous() if has_groups else None
+                _C.check(lib.cvdb_selfjoin_cross(local._h, qh.data_ptr(), hm, dt, ids.data_ptr(),
+                                                 gh.data_ptr() if has_groups else None, int(row_begin), int(row_end),
+                                                 bases[g], send[h].data_ptr(), stream))
+                return 1
+
+            for dd in range(1, full_d + 1):
+                n_blocks += cross((g + dd) % G, 0, 0)
+            if G % 2 == 0 and G > 1:
+                h = (g + G // 2) % G
+                if g < h:                       # lower rank of the pair: every anchor chunk of h x my first half
+                    if half_row[g] > 0:
+                        n_blocks += cross(h, 0, half_row[g])
+                elif s_i >= half_idx[h]:        # upper rank: the second-half anchor chunks of h x all my rows
+                    n_blocks += cross(h, 0, 0)
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv.view(G * m_max, k), send.view(G * m_max, k), group=index.group)
+            if m:
+                merged = torch.empty((m_max, k), dtype=torch.int64, device=dev)
+                _C.check(lib.cvdb_merge_keys(recv.data_ptr(), m_max, G, k, k, merged.data_ptr(), stream))
+                row_keys[r0:r0 + m] = merged[:m]
+        D = torch.empty((n_loc, k), dtype=torch.float32, device=dev)
+        I = torch.empty((n_loc, k), dtype=torch.int64, device=dev)
+        max_dirty = max(1, min(n_loc, 1 << 22))
+        rows = torch.empty((max_dirty,), dtype=torch.int32, device=dev)
+        nd = _C.C.c_int64(0)
+        if n_loc:
+            _C.check(lib.cvdb_selfjoin_finish(local._h, 0, n_loc, row_keys.data_ptr(), D.data_ptr(), I.data_ptr(), stream))
+            _C.check(lib.cvdb_selfjoin_dirty(local._h, rows.data_ptr(), max_dirty, _C.C.byref(nd), stream))
+        del row_keys
+    finally:
+        _C.check(lib.cvdb_selfjoin_end(local._h))
+    # ---- rows that lost column candidates anywhere: recomputed by the plain sharded search, owner by owner
+    n_dirty = int(nd.value)
+    if n_dirty > max_dirty:
+        rows, n_dirty = torch.arange(n_loc, device=dev, dtype=torch.int32), n_loc
+    rows = rows[:n_dirty].sort().values.long()
+    tot = torch.tensor([n_dirty], dtype=torch.int64, device=dev)
+    all_n = [torch.zeros_like(tot) for _ in range(G)]
+    dist.all_gather(all_n, tot, group=index.group)
+    all_n = [int(t.item()) for t in all_n]
+    if stats is not None:
+        stats.update(steps=steps, blocks=n_blocks, dirty_rows=n_dirty, dirty_rows_all_ranks=sum(all_n))
+    for owner in range(G):
+        src = dist.get_global_rank(index.group, owner) if index.group is not None else owner
+        for q0 in range(0, all_n[owner], 65536):
+            mq = min(65536, all_n[owner] - q0)
+            if g == owner:
+                rr = rows[q0:q0 + mq]
+                q = local_emb[rr].contiguous()
+                ids = (rr + bases[g]).contiguous()
+                gq = grp_dev[rr].contiguous() if has_groups else None
+            else:
+                q = torch.empty((mq, d), dtype=local_emb.dtype, device=dev)
+                ids = torch.empty((mq,), dtype=torch.int64, device=dev)
+                gq = torch.empty((mq,), dtype=torch.int32, device=dev) if has_groups else None
+            dist.broadcast(q, src=src, group=index.group)
+            dist.broadcast(ids, src=src, group=index.group)
+            if has_groups:
+                dist.broadcast(gq, src=src, group=index.group)
+            Dq, Iq = index.search(q, k, self_ids=ids, group_q=gq)
+            if g == owner:
+                D[rr], I[rr] = Dq, Iq
+    return D, I
 
 
 def build_triplets(D, I, positives, *, skip_top: int = 0, per_anchor: int = 1, metric: str = "ip",

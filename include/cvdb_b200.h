@@ -76,8 +76,9 @@ typedef struct cvdb_search_opts {
                                 8 = no wave alignment of the producers, 16 = run all K-steps of the padded row width,
                                 32 = always sort the whole candidate buffer at the end of a work item,
                                 64 = small batches: fill the query tile from row 0 up instead of one quarter per
-                                epilogue warp, 128 = every database slice starts from an empty candidate buffer instead
-                                of the result of an earlier slice (4, 8, 16, 32, 64 and 128 leave the results valid) */
+                                epilogue warp, 128 = every database slice starts from the result list of the latest finished
+                                earlier slice of its query tile instead of an empty candidate buffer (4, 8, 16, 32, 64
+                                and 128 leave the results valid) */
 } cvdb_search_opts;
 
 /* -- index lifetime -------------------------------------------------------
@@ -177,6 +178,8 @@ int cvdb_index_search_keys(cvdb_index_t idx, const void* q, int64_t nq, int dtyp
                            const cvdb_search_opts* opts, void* stream);
 int cvdb_index_merge_keys(cvdb_index_t idx, const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, float* D,
                           int64_t* I, void* stream);
+/* the same merge with the result left in keys [nq][k] (lists of lists: merging what several steps produced) */
+int cvdb_merge_keys(const uint64_t* keys, int64_t nq, int nlists, int k_in, int k, uint64_t* keys_out, void* stream);
 
 /* -- symmetric self-join (hard-negative mining over the index's OWN rows; README.md:2 "dataset of triplets") -----
  * A self-join computes every score twice: (anchor i, row j) and (anchor j, row i).  These calls compute each tile of
@@ -190,14 +193,21 @@ int cvdb_index_merge_keys(cvdb_index_t idx, const uint64_t* keys, int64_t nq, in
  *   chunk   anchors = rows [row0, row0 + nrows), row0 a multiple of 128, nrows <= 65536, chunks in increasing row order
  *           and contiguous; writes the row-direction result of the chunk as keys [nrows][k] (see cvdb_index_search_keys).
  *           Chunk sizes should start small and at most double (256, 256, 512, 1024, ...): a row's buffer takes the
- *           candidates of ONE chunk under the threshold of the chunks before it
+ *           candidates of ONE chunk under the threshold of the chunks before it.  id_base is added to every id that
+ *           leaves the index (row-direction keys, and the anchors' ids in the column lists): the shard offset
+ *   cross   the block (anchors of ANOTHER shard) x (rows [row_begin, row_end) of this index; row_end <= 0: ntotal):
+ *           q [nq][d] are the anchors' vectors, q_ids [nq] their global ids, group_q [nq] their groups (or NULL);
+ *           row direction -> keys [nq][k] with ids + id_base, column direction -> the lists of this index's rows.
+ *           One of the two shards of a pair computes the block; the other receives the keys (see sharded.py)
  *   finish  merges the row-direction keys of rows [row0, row0 + nrows) with their column lists -> D, I (any row range,
  *           after the last chunk)
  *   dirty   rows whose column buffer overflowed (their lists lost candidates): writes up to max_out row ids, returns
  *           the count; the caller recomputes those rows with cvdb_index_search (exact, with the same exclusion)
  *   end     frees the join state */
 int cvdb_selfjoin_begin(cvdb_index_t idx, int k, void* stream);
-int cvdb_selfjoin_chunk(cvdb_index_t idx, int64_t row0, int64_t nrows, uint64_t* keys, void* stream);
+int cvdb_selfjoin_chunk(cvdb_index_t idx, int64_t row0, int64_t nrows, int64_t id_base, uint64_t* keys, void* stream);
+int cvdb_selfjoin_cross(cvdb_index_t idx, const void* q, int64_t nq, int dtype, const int32_t* q_ids, const int32_t* group_q,
+                        int64_t row_begin, int64_t row_end, int64_t id_base, uint64_t* keys, void* stream);
 int cvdb_selfjoin_finish(cvdb_index_t idx, int64_t row0, int64_t nrows, const uint64_t* row_keys, float* D, int64_t* I,
                          void* stream);
 int cvdb_selfjoin_dirty(cvdb_index_t idx, int32_t* rows_out, int64_t max_out, int64_t* n_out, void* stream);

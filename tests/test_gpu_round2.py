@@ -284,8 +284,8 @@ def test_handleless_calls_run_on_the_device_that_owns_the_data():
 @pytest.mark.parametrize("variant,k", [(1, 10), (2, 50), (3, 100), (2, 200), (1, 20)])
 def test_slice_inheritance_is_result_neutral(variant, k):
     """Many database slices (more than 32, so merge lanes own several lists), slices long enough to inherit: the
-    lists of different slices overlap and the merge must drop the copies.  Same answer with inheritance off
-    (debug flag 128), and equal to the oracle; with exclusion as well."""
+    lists of different slices overlap and the merge must drop the copies.  Same answer with inheritance on
+    (debug flag 128) and off, and equal to the oracle; with exclusion as well."""
     from cloudvectordb_b200 import IndexFlat
     rng = np.random.default_rng(variant * 100 + k)
     n, d, nq = 400_000, 64, 300
@@ -297,9 +297,9 @@ def test_slice_inheritance_is_result_neutral(variant, k):
     idx = IndexFlat(d, "ip", "bf16", 0)
     idx.add(xb)
     slices = 40 if variant != 1 else 45
-    D, I = idx.search(xq, k, force_variant=variant, force_slices=slices)
+    D, I = idx.search(xq, k, force_variant=variant, force_slices=slices, debug_flags=128)   # inheritance on
     assert idx.last_work()["n_slices"] >= 33
-    D0, I0 = idx.search(xq, k, force_variant=variant, force_slices=slices, debug_flags=128)
+    D0, I0 = idx.search(xq, k, force_variant=variant, force_slices=slices)
     assert np.array_equal(I, I0) and np.array_equal(D, D0)
     D_ref, I_ref = O.search_ref(xb, xq, k, O.METRIC_IP)
     assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
@@ -308,7 +308,8 @@ def test_slice_inheritance_is_result_neutral(variant, k):
     idx.set_groups(groups)
     self_ids = rng.integers(0, n, nq).astype(np.int32)
     gq = groups[self_ids]
-    D, I = idx.search(xb[self_ids], k, self_ids=self_ids, group_q=gq, force_variant=variant, force_slices=slices)
+    D, I = idx.search(xb[self_ids], k, self_ids=self_ids, group_q=gq, force_variant=variant, force_slices=slices,
+                      debug_flags=128)
     D_ref, I_ref = O.search_ref(xb, xb[self_ids], k, O.METRIC_IP, self_ids=self_ids, group_db=groups, group_q=gq)
     assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
     idx.close()

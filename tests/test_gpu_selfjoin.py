@@ -127,11 +127,11 @@ def test_selfjoin_argument_checks():
     idx.close()
     idx = IndexFlat(32, "ip", "bf16", 0)
     idx.add(np.ones((300, 32), np.float32))
-    assert lib.cvdb_selfjoin_chunk(idx._h, 0, 256, 1, None) == _C.EINVAL    # no join open
+    assert lib.cvdb_selfjoin_chunk(idx._h, 0, 256, 0, 1, None) == _C.EINVAL    # no join open
     assert lib.cvdb_selfjoin_begin(idx._h, 1, None) == _C.ELIMIT
     assert lib.cvdb_selfjoin_begin(idx._h, 10, None) == 0
     keys = torch.empty((300, 10), dtype=torch.int64, device="cuda")
-    assert lib.cvdb_selfjoin_chunk(idx._h, 64, 100, keys.data_ptr(), None) == _C.EINVAL   # unaligned start
-    assert lib.cvdb_selfjoin_chunk(idx._h, 256, 100, keys.data_ptr(), None) == _C.EINVAL  # past the end
+    assert lib.cvdb_selfjoin_chunk(idx._h, 64, 100, 0, keys.data_ptr(), None) == _C.EINVAL   # unaligned start
+    assert lib.cvdb_selfjoin_chunk(idx._h, 256, 100, 0, keys.data_ptr(), None) == _C.EINVAL  # past the end
     assert lib.cvdb_selfjoin_end(idx._h) == 0
     idx.close()

@@ -1,0 +1,71 @@
+"""Whole self-join (hard-negative mining, k = 50, self + group-of-4 exclusion) of an n x 768 bf16 matrix on one GPU:
+the plain join (every anchor chunk against every row) against the symmetric join (every tile of X.X^T once, both
+directions).  Reports seconds, the rate on the full 2*n^2*d count, and whether the two results agree.
+
+    python tools/selfjoin_bench.py [--rows 2000000] [--k 50] [--out gpurun_out/selfjoin.jsonl]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bench import gen_rows  # noqa: E402
+from cloudvectordb_b200 import IndexFlat, mine_hard_negatives, mine_hard_negatives_symmetric  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=2_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--skip-plain", action="store_true")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "selfjoin.jsonl"))
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    emb = gen_rows(torch, dev, 1234, 0, a.rows, a.dim, torch.bfloat16)
+    groups = (torch.arange(a.rows, device=dev) // 4).to(torch.int32)
+    idx = IndexFlat(a.dim, "ip", "bf16")
+    idx.reserve(a.rows)
+    idx.add(emb)
+    idx.set_groups(groups)
+    flops = 2.0 * a.rows * a.rows * a.dim
+    rec = {"rows": a.rows, "dim": a.dim, "k": a.k, "exclusion": "self + group of 4", "flops_full_count": flops}
+    # warm both paths on a small prefix
+    small = IndexFlat(a.dim, "ip", "bf16")
+    small.add(emb[:70_000])
+    small.set_groups(groups[:70_000])
+    mine_hard_negatives_symmetric(small, a.k, emb=emb[:70_000], groups=groups[:70_000])
+    mine_hard_negatives(emb[:70_000], a.k, groups[:70_000], index=small)
+    small.close()
+    torch.cuda.synchronize()
+    stats = {}
+    t0 = time.perf_counter()
+    Ds, Is = mine_hard_negatives_symmetric(idx, a.k, emb=emb, groups=groups, stats=stats)
+    torch.cuda.synchronize()
+    ts = time.perf_counter() - t0
+    rec.update(symmetric_s=ts, symmetric_tflops_on_full_count=flops / ts / 1e12, symmetric_stats=stats)
+    if not a.skip_plain:
+        t0 = time.perf_counter()
+        Dp, Ip = mine_hard_negatives(emb, a.k, groups, index=idx)
+        torch.cuda.synchronize()
+        tp = time.perf_counter() - t0
+        same = float((Is == Ip).float().mean())
+        bad = int(((Is != Ip) & ((Ds - Dp).abs() > 2e-5)).sum())
+        rec.update(plain_s=tp, plain_tflops=flops / tp / 1e12, speedup=tp / ts, ids_equal_fraction=same,
+                   mismatch_beyond_tie_2e5=bad)
+    idx.close()
+    line = json.dumps(rec)
+    print(line, flush=True)
+    with open(a.out, "a") as f:
+        f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
