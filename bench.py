@@ -17,7 +17,8 @@ copy of the queries and device->host copy of (D, I) inside the timed region).
 `roofline` block:
     configs[0]  exact top-10 IP, 100k x 384 fp32, 10k queries                    (replica per rank)
     configs[2]  one 65 536-anchor hard-negative mining chunk, k=50, self + group exclusion, against the
-                headline database (rows split over the N ranks)
+                headline database (rows split over the N ranks); and the WHOLE self-join of 1M rows per rank, plain
+                against symmetric (every tile of X.X^T computed once)
     configs[3]  one Lloyd iteration, 100M x 384 points split over the N ranks, 65 536 centroids
     configs[4]  small-batch latency, nq in {1, 16, 64}, 12.5M x 768 rows PER rank, >= 200 distinct batches
     ingest      host -> HBM add() rate, fp32 rows, pageable and pinned source (N = 1 only)
@@ -60,6 +61,7 @@ def parse():
     ap.add_argument("--configs", default="all", help="all | none | comma list of 0,2,3,4,ingest")
     ap.add_argument("--km-points", type=int, default=100_000_000, help="configs[3]: points in total (split over the ranks)")
     ap.add_argument("--lat-rows", type=int, default=12_500_000, help="configs[4]: database rows PER rank")
+    ap.add_argument("--sj-rows", type=int, default=1_000_000, help="configs[2] whole self-join: rows PER rank")
     ap.add_argument("--dbg", type=int, default=0, help="kernel debug flags (tuning experiments)")
     ap.add_argument("--slices", type=int, default=0, help="override the database-slice heuristic")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 streaming kernel, 2 CTA-pair/TMEM kernel")
@@ -489,6 +491,70 @@ def run_ours(a):
                 "whole_50M_join_estimate_s_on_8_gpus": (50_000_000 / n_anchor) * (ms / 1e3) * (6_250_000 / rows_local),
                 "estimate_note": "chunk time scaled by rows to the 6.25M-row shard of configs[2] x 763 chunks; full 2*N^2*d count"}
 
+    def cfg_selfjoin():
+        """configs[2], the whole job on a bounded corpus: self-join top-50 (self + group-of-4 exclusion) of sj_rows rows
+        PER rank (the first rows of every rank's shard of the headline matrix), plain (every anchor chunk against
+        every row: 2*n^2*d flops) against symmetric (every tile of X.X^T once, selected in both directions; across
+        ranks one rank of every shard pair computes the block).  Same answer, about half the time."""
+        from cloudvectordb_b200 import (mine_hard_negatives, mine_hard_negatives_sharded,
+                                        mine_hard_negatives_sharded_symmetric, mine_hard_negatives_symmetric)
+        k = 50
+        n_loc = min(a.sj_rows, hi - lo)
+        emb = xb[:n_loc]
+        if world > 1:
+            sj = ShardedIndex(a.dim, "ip", "bf16", device=local_rank)
+            sj.local.reserve(n_loc)
+            sj.add_local(emb)
+            base = sj.id_base
+            n_tot = sj.ntotal
+        else:
+            sj = IndexFlat(a.dim, "ip", "bf16", device=local_rank)
+            sj.reserve(n_loc)
+            sj.add(emb)
+            base, n_tot = 0, n_loc
+        groups = ((torch.arange(n_loc, device=dev) + base) // 4).to(torch.int32)
+        (sj.set_groups_local if world > 1 else sj.set_groups)(groups)
+
+        def plain():
+            if world > 1:
+                return mine_hard_negatives_sharded(sj, emb, k, groups)
+            return mine_hard_negatives(emb, k, groups, index=sj)
+
+        st_ = {}
+
+        def symmetric():
+            if world > 1:
+                return mine_hard_negatives_sharded_symmetric(sj, emb, k, groups, stats=st_)
+            return mine_hard_negatives_symmetric(sj, k, emb=emb, groups=groups, stats=st_)
+
+        def clock(fn):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            barrier()
+            return max_over_ranks(ms) / 1e3, out
+        ts, (Ds, Is) = clock(symmetric)
+        tp, (Dp, Ip) = clock(plain)
+        same = float((Is == Ip).float().mean())
+        bad = int(((Is != Ip) & ((Ds - Dp).abs() > 2e-5)).sum())
+        (sj.local if world > 1 else sj).close()
+        flops = 2.0 * n_tot * n_tot * a.dim
+        tf_gpu = flops / ts / 1e12 / world
+        return {"config": "configs[2] whole self-join on a bounded corpus, plain vs symmetric", "rows_total": n_tot,
+                "rows_per_gpu": n_loc, "k": k, "exclusion": "self + group of 4", "plain_s": tp, "symmetric_s": ts,
+                "speedup": tp / ts, "ids_equal_fraction_on_rank0_rows": same, "mismatch_beyond_tie_2e-5_on_rank0_rows": bad,
+                "symmetric_stats": st_,
+                "roofline": {"bound": "tensor", "achieved": tf_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_gpu / peak_tf,
+                             "per": "GPU, whole join incl. exchanges and merges, on the FULL 2*n^2*d count",
+                             "note": "the symmetric join issues half of these flops (SURVEY.md 8(d): 'would show as > 1x on this "
+                                     "count'); plain join on the same count: %.1f TFLOP/s per GPU" % (flops / tp / 1e12 / world)},
+                "whole_50M_join_estimate_s_on_8_gpus": ts * (50_000_000 / n_tot) ** 2 * (world / 8.0),
+                "estimate_note": "symmetric_s scaled by (50M / rows_total)^2 and by n_gpus / 8"}
+
     def cfg_latency():
         """configs[4]: small-batch latency against lat_rows rows PER rank (100M x 768 over 8 GPUs = 12.5M each):
         >= 200 DISTINCT query batches per size, per-call device time (CUDA events) and wall time (with a
@@ -644,6 +710,7 @@ def run_ours(a):
 
     if "2" in which:
         guarded("configs[2]", cfg_mining)
+        guarded("configs[2] symmetric", cfg_selfjoin)
     if "4" in which:
         guarded("configs[4]", cfg_latency)
     # the headline database is no longer needed: free it before the 76.8 GB k-means matrix

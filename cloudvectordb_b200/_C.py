@@ -76,8 +76,9 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p]),
     "cvdb_selfjoin_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cvdb_selfjoin_chunk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cvdb_selfjoin_seed": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cvdb_selfjoin_cross": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                      C.c_int64, C.c_void_p, C.c_void_p]),
+                                      C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cvdb_merge_keys": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvdb_selfjoin_finish": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvdb_selfjoin_dirty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),

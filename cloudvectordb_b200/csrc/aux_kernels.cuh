@@ -561,6 +561,32 @@ __global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __r
     }
 }
 
+// Seeding: the sorted top-k keys of row r among the seed anchors (a plain row-direction search) become the first
+// entries of its column list; a full list sets the row's threshold.  One warp per row.
+__global__ void col_seed_kernel(const uint64_t* __restrict__ keys, int64_t row0, int64_t n, int k,
+                                uint64_t* __restrict__ col_buf, uint32_t* __restrict__ col_cnt,
+                                uint32_t* __restrict__ col_base, float* __restrict__ col_thr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int64_t r = row0 + i;
+    int cnt = 0;
+    for (int pos = lane; pos < k; pos += 32) {
+        const uint64_t key = keys[i * k + pos];
+        col_buf[r * kColCap + pos] = key;
+        cnt += key != 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) {
+        col_cnt[r] = cnt;
+        col_base[r] = cnt;
+        if (cnt >= k) {
+            const uint32_t ord = static_cast<uint32_t>(keys[i * k + k - 1] >> 32);
+            col_thr[r] = ord == 0x80000000u ? -1.17549435e-38f : ordered_to_float(ord - 1u);
+        }
+    }
+}
+
 // Final answer of anchor i = top-k of (its row-direction keys, sorted, k of them) and (its column list, <= k keys,
 // unsorted).  The two sets are disjoint (rows at or after the anchor's chunk / anchors of earlier chunks).
 // One warp per anchor; k <= 124.

@@ -1456,8 +1456,52 @@ int cvdb_selfjoin_chunk(cvdb_index_t h, int64_t row0, int64_t nrows, int64_t id_
     return selfjoin_compact(ix, row0 + nrows, ix->ntotal, st);
 }
 
+int cvdb_selfjoin_seed(cvdb_index_t h, int64_t seed_rows, int64_t id_base, uint64_t* keys_seed, void* stream) {
+    TRY(check_index(h));
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
+    if (seed_rows < 1 || seed_rows > 65536 || seed_rows > ix->ntotal || (seed_rows % 128 && seed_rows != ix->ntotal))
+        return fail(CVDB_EINVAL, "seed_rows must be a multiple of 128 in [128, min(65536, ntotal)] (or all rows)");
+    if (id_base < 0 || id_base + ix->ntotal > 0xFFFFFFFELL) return fail(CVDB_ELIMIT, "ids must stay below 2^32 - 1");
+    cvdb_guard g(ix->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamOrder order(ix, st);
+    const int k = ix->sj_k;
+    cvdb_search_opts o{};
+    o.id_base = id_base;
+    const int32_t* groups = ix->has_groups ? ix->groups.as<int32_t>() : nullptr;
+    if (keys_seed) {
+        // (a) the seed anchors themselves: a plain search of rows [0, seed_rows) over ALL rows of this index
+        TRY(ix->ids_a.ensure(static_cast<size_t>(seed_rows) * 4));
+        iota_kernel<<<static_cast<unsigned>(ceil_div(seed_rows, 256)), 256, 0, st>>>(ix->ids_a.as<int32_t>(), 0, seed_rows);
+        ++g_launches;
+        SearchExtra ex;
+        ex.q_packed = ix->x;
+        ex.q_rows_avail = ix->ntotal;
+        TRY(search_device(ix, nullptr, seed_rows, CVDB_DTYPE_BF16, k, nullptr, nullptr, nullptr, ix->ids_a.as<int32_t>(), groups, &o,
+                          st, keys_seed, nullptr, &ex));
+    }
+    // (b) every later row: its top-k among the seed anchors starts its column list (and its threshold)
+    TRY(ix->out_i.ensure(static_cast<size_t>(65536) * k * 8));
+    for (int64_t q0 = seed_rows; q0 < ix->ntotal; q0 += 65536) {
+        const int64_t m = std::min<int64_t>(65536, ix->ntotal - q0);
+        SearchExtra ex;
+        ex.q_packed = ix->x + q0 * ix->row_elems;
+        ex.q_rows_avail = ix->ntotal - q0;
+        ex.row_end = seed_rows;
+        TRY(search_device(ix, nullptr, m, CVDB_DTYPE_BF16, k, nullptr, nullptr, nullptr, nullptr, groups ? groups + q0 : nullptr, &o,
+                          st, ix->out_i.as<uint64_t>(), nullptr, &ex));
+        col_seed_kernel<<<static_cast<unsigned>(ceil_div(m, 8)), 256, 0, st>>>(ix->out_i.as<uint64_t>(), q0, m, k,
+                                                                              ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
+                                                                              ix->col_base.as<uint32_t>(), ix->col_thr.as<float>());
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+    }
+    return CVDB_OK;
+}
+
 int cvdb_selfjoin_cross(cvdb_index_t h, const void* q, int64_t nq, int dtype, const int32_t* q_ids, const int32_t* group_q,
-                        int64_t row_begin, int64_t row_end, int64_t id_base, uint64_t* keys, void* stream) {
+                        int64_t row_begin, int64_t row_end, int64_t col_row_min, int64_t id_base, uint64_t* keys, void* stream) {
     TRY(check_index(h));
     Index* ix = reinterpret_cast<Index*>(h);
     if (ix->sj_k < 2) return fail(CVDB_EINVAL, "no self-join is open (cvdb_selfjoin_begin)");
@@ -1478,12 +1522,12 @@ int cvdb_selfjoin_cross(cvdb_index_t h, const void* q, int64_t nq, int dtype, co
     ex.row_begin = row_begin;
     ex.row_end = row_end;
     ex.col = true;
-    ex.col_row_min = row_begin;
+    ex.col_row_min = std::max(row_begin, col_row_min);
     ex.q_ids = q_ids;
     cvdb_search_opts o{};
     o.id_base = id_base;
     TRY(search_device(ix, q, nq, dtype, ix->sj_k, nullptr, nullptr, nullptr, nullptr, group_q, &o, st, keys, nullptr, &ex));
-    return selfjoin_compact(ix, row_begin, row_end, st);
+    return selfjoin_compact(ix, ex.col_row_min, row_end, st);
 }
 
 int cvdb_selfjoin_finish(cvdb_index_t h, int64_t row0, int64_t nrows, const uint64_t* row_keys, float* D, int64_t* I,

@@ -257,7 +257,8 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room, cons
 // groups of 8 in which some lane has a candidate are walked element by element.
 template <int E>
 __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0, uint32_t row_end,
-                                           uint32_t self, int grp, const int32_t* __restrict__ group_db, int k, int room) {
+                                           uint32_t self, int grp, const int32_t* __restrict__ group_db, int k, int room,
+                                           float* m_out = nullptr) {
     float m8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -267,6 +268,7 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
         m8[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
     }
     const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    if (m_out != nullptr) *m_out = m;  // the column direction of the symmetric join tests the same maximum
     if (!__any_sync(0xffffffffu, m > st.thr)) return;  // common case once the threshold has settled
     if constexpr (E >= 2) {
         // Buffers of 64+ slots: make room for a whole chunk (32 candidates) once, then let only the lanes that
@@ -979,18 +981,6 @@ __device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], float m,
         }
     }
 }
-__device__ __forceinline__ float chunk_max32(const uint32_t (&v)[32]) {
-    float m4[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float m = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
-        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 3])), __uint_as_float(v[8 * g + 4]));
-        m = fmaxf(fmaxf(m, __uint_as_float(v[8 * g + 5])), __uint_as_float(v[8 * g + 6]));
-        m4[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
-    }
-    return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-}
-
 // ===========================================================================
 // CTA pair (cta_group::2, M = 256) with the QUERIES RESIDENT ON CHIP.
 //
@@ -1289,15 +1279,17 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
                     }
+                    float m_chunk = -INFINITY;
                     if (!(dbg & 3))
-                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room);
+                        scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room,
+                                      COL ? &m_chunk : nullptr);
                     if constexpr (COL) {
                         float ct = cthr[0], cm = cmin[0];  // (the loop is not unrolled: pick the chunk's registers)
 #pragma unroll
                         for (int q = 1; q < BLOCK_N / 32; ++q)
                             if (c == q * 32) { ct = cthr[q]; cm = cmin[q]; }
                         if (cm < INFINITY)  // warp-uniform: some row of the chunk collects
-                            scan_chunk_col(v, chunk_max32(v), ct, cm, row0 + c, anchor_id, self, grp, q_valid, p);
+                            scan_chunk_col(v, m_chunk, ct, cm, row0 + c, anchor_id, self, grp, q_valid, p);
                     }
                 }
                 acc ^= 1;

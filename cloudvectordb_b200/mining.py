@@ -19,7 +19,8 @@ except Exception:  # pragma: no cover
 
 def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, metric: str = "ip",
                         storage: str = "bf16", device: int = 0, chunk: int = 65536, index=None,
-                        row_offset: int = 0, queries=None, query_groups=None, symmetric: bool = False):
+                        row_offset: int = 0, queries=None, query_groups=None, symmetric: bool = False,
+                        first_chunk: int = 8192):
     """Top-k most similar rows of `emb` for every row (or for `queries`), never
     returning the anchor row itself nor any row with the anchor's group id.
 
@@ -40,7 +41,7 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
         # every tile of X.X^T once, selected in both directions (half the flops); whole-matrix self-join only
         if queries is not None or not exclude_self or metric.lower() != "ip" or storage.lower() != "bf16" or row_offset:
             raise ValueError("symmetric=True is the plain self-join: IP metric, bf16 storage, all rows as anchors")
-        D, I = mine_hard_negatives_symmetric(index, k, emb=emb, groups=groups, chunk=chunk)
+        D, I = mine_hard_negatives_symmetric(index, k, emb=emb, groups=groups, chunk=chunk, first_chunk=first_chunk)
         if own:
             index.close()
         if _is_torch(emb) and emb.is_cuda:
@@ -66,9 +67,10 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
     return np.concatenate(outs_d), np.concatenate(outs_i)
 
 
-def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 256):
-    """Anchor chunks of the symmetric self-join: (row0, rows) in row order, sizes 256, 256, 512, 1024, ... (each at
-    most the number of rows before it, so a row's column buffer sees about k new candidates per chunk) up to `chunk`."""
+def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 8192):
+    """Anchor chunks of the symmetric self-join: (row0, rows) in row order.  Chunk 0 is the SEED region (handled by
+    plain searches, cvdb_selfjoin_seed); every later chunk is at most as long as the rows before it (so a row's
+    column buffer sees about k new candidates per chunk) and at most `chunk`."""
     out, r = [], 0
     while r < n:
         m = min(first if r == 0 else min(chunk, r), n - r)
@@ -78,23 +80,32 @@ def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 256):
 
 
 def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=None, chunk: int = 65536,
-                                  first_chunk: int = 256, stats: Optional[dict] = None):
+                                  first_chunk: int = 8192, stats: Optional[dict] = None):
     """Self-join top-k over ALL rows of `index` (IP, bf16 storage, groups already set with set_groups) that computes
     every tile of X.X^T once and selects in both directions (include/cvdb_b200.h, cvdb_selfjoin_*): half the flops
-    of mine_hard_negatives().  Rows whose column buffer overflowed (adversarial row orders) are recomputed exactly
-    with a plain search; that needs `emb` (and `groups`).  Returns (D [n, k] f32, I [n, k] i64) on the GPU."""
+    of mine_hard_negatives().  The first `first_chunk` rows are the seed (plain searches warm the column side up).
+    Rows whose column buffer overflowed (adversarial row orders) are recomputed exactly with a plain search; that
+    needs `emb` (and `groups`).  Returns (D [n, k] f32, I [n, k] i64) on the GPU."""
     lib = _C.lib()
     n = index.ntotal
     dev = torch.device("cuda", index.device)
     stream = int(torch.cuda.current_stream(index.device).cuda_stream)
-    if chunk % 256 or first_chunk % 256:
-        raise ValueError("chunk sizes must be multiples of 256")
+    if chunk % 256 or first_chunk % 256 or first_chunk > 65536:
+        raise ValueError("chunk sizes must be multiples of 256 (the seed at most 65536)")
     _C.check(lib.cvdb_selfjoin_begin(index._h, int(k), stream))
     try:
         keys = torch.empty((n, k), dtype=torch.int64, device=dev)
         sched = selfjoin_schedule(n, chunk, first_chunk)
-        for r0, m in sched:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(sched) + 1)] if stats is not None else None
+        if ev:
+            ev[0].record()
+        _C.check(lib.cvdb_selfjoin_seed(index._h, sched[0][1], 0, keys.data_ptr(), stream))
+        if ev:
+            ev[1].record()
+        for i, (r0, m) in enumerate(sched[1:]):
             _C.check(lib.cvdb_selfjoin_chunk(index._h, r0, m, 0, keys[r0:].data_ptr(), stream))
+            if ev:
+                ev[i + 2].record()
         D = torch.empty((n, k), dtype=torch.float32, device=dev)
         I = torch.empty((n, k), dtype=torch.int64, device=dev)
         _C.check(lib.cvdb_selfjoin_finish(index._h, 0, n, keys.data_ptr(), D.data_ptr(), I.data_ptr(), stream))
@@ -107,7 +118,8 @@ def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=
         _C.check(lib.cvdb_selfjoin_end(index._h))
     n_dirty = int(nd.value)
     if stats is not None:
-        stats.update(chunks=len(sched), dirty_rows=n_dirty)
+        stats.update(chunks=len(sched), dirty_rows=n_dirty, schedule=[m for _, m in sched],
+                     step_ms=[round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(len(sched))])
     if n_dirty:
         # exact recomputation of the rows that lost column candidates (plain row-direction search of the whole index)
         if emb is None:
@@ -169,7 +181,7 @@ def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, 
 
 
 def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups=None, *, chunk: int = 65536,
-                                          first_chunk: int = 256, stats: Optional[dict] = None):
+                                          first_chunk: int = 8192, stats: Optional[dict] = None):
     """The symmetric self-join over a ShardedIndex (one process per GPU, NCCL): every unordered pair of rows is
     scored once in the whole job.
 
@@ -182,7 +194,8 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     (all its rows).  The diagonal block is the single-GPU symmetric join (cvdb_selfjoin_chunk).  Every rank does
     (G/2)/G of the plain job's flops.
 
-    Steps.  All owners walk the same doubling chunk schedule (selfjoin_schedule); step s: all-gather chunk s of every
+    Steps.  All owners walk the same chunk schedule (selfjoin_schedule: a seed chunk handled by plain searches, then
+    chunks that at most double); step s: all-gather chunk s of every
     owner (vectors, groups), each rank runs its 1 + (G-1)/2 (+1/2) blocks, the row-direction keys go to the
     anchors' owners with ONE all_to_all, and the owner merges the G lists into its running row keys.  After the last
     step cvdb_selfjoin_finish merges row keys and column lists.  Rows whose column buffer overflowed anywhere are
@@ -198,7 +211,10 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     bases = [sum(counts[:h]) for h in range(G)]
     n_loc, d = counts[g], int(local_emb.shape[1])
     stream = int(torch.cuda.current_stream(dev.index).cuda_stream)
+    if chunk % 256 or first_chunk % 256 or first_chunk > 65536:
+        raise ValueError("chunk sizes must be multiples of 256 (the seed at most 65536)")
     sched = [selfjoin_schedule(c, chunk, first_chunk) for c in counts]
+    seed = [sc[0][1] if sc else 0 for sc in sched]       # rows [0, seed[h]) of shard h: handled by plain searches
     steps = max(len(sc) for sc in sched)
     # the chunk boundary nearest to the middle of every shard (the row split of the distance-G/2 pairs)
     half_idx = [min(range(len(sc)), key=lambda i: abs(sc[i][0] - c // 2)) if sc else 0 for sc, c in zip(sched, counts)]
@@ -210,6 +226,8 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     n_blocks = 0
     try:
         row_keys = torch.zeros((n_loc, k), dtype=torch.int64, device=dev)
+        if n_loc:   # column lists of my later rows start with their top-k among my seed anchors
+            _C.check(lib.cvdb_selfjoin_seed(local._h, seed[g], bases[g], None, stream))
         for s_i in range(steps):
             ch = [sc[s_i] if s_i < len(sc) else (0, 0) for sc in sched]
             m_max = max(m for _, m in ch)
@@ -225,7 +243,7 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
             dist.all_gather_into_tensor(Q.view(G * m_max, d), q_mine, group=index.group)
             dist.all_gather_into_tensor(GR.view(-1), g_mine, group=index.group)
             send = torch.zeros((G, m_max, k), dtype=torch.int64, device=dev)
-            if m:   # the diagonal block
+            if m and s_i > 0:   # the diagonal block (chunk 0, the seed anchors, gets the plain sharded search below)
                 _C.check(lib.cvdb_selfjoin_chunk(local._h, r0, m, bases[g], send[g].data_ptr(), stream))
                 n_blocks += 1
 
@@ -239,7 +257,7 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
                 gh = GR[h, :hm].contiguous() if has_groups else None
                 _C.check(lib.cvdb_selfjoin_cross(local._h, qh.data_ptr(), hm, dt, ids.data_ptr(),
                                                  gh.data_ptr() if has_groups else None, int(row_begin), int(row_end),
-                                                 bases[g], send[h].data_ptr(), stream))
+                                                 seed[g], bases[g], send[h].data_ptr(), stream))
                 return 1
 
             for dd in range(1, full_d + 1):
@@ -253,7 +271,7 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
                     n_blocks += cross(h, 0, 0)
             recv = torch.empty_like(send)
             dist.all_to_all_single(recv.view(G * m_max, k), send.view(G * m_max, k), group=index.group)
-            if m:
+            if m and s_i > 0:
                 merged = torch.empty((m_max, k), dtype=torch.int64, device=dev)
                 _C.check(lib.cvdb_merge_keys(recv.data_ptr(), m_max, G, k, k, merged.data_ptr(), stream))
                 row_keys[r0:r0 + m] = merged[:m]
@@ -262,8 +280,10 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
         max_dirty = max(1, min(n_loc, 1 << 22))
         rows = torch.empty((max_dirty,), dtype=torch.int32, device=dev)
         nd = _C.C.c_int64(0)
+        if n_loc > seed[g]:
+            _C.check(lib.cvdb_selfjoin_finish(local._h, seed[g], n_loc - seed[g], row_keys[seed[g]:].data_ptr(),
+                                              D[seed[g]:].data_ptr(), I[seed[g]:].data_ptr(), stream))
         if n_loc:
-            _C.check(lib.cvdb_selfjoin_finish(local._h, 0, n_loc, row_keys.data_ptr(), D.data_ptr(), I.data_ptr(), stream))
             _C.check(lib.cvdb_selfjoin_dirty(local._h, rows.data_ptr(), max_dirty, _C.C.byref(nd), stream))
         del row_keys
     finally:
@@ -273,12 +293,15 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     if n_dirty > max_dirty:
         rows, n_dirty = torch.arange(n_loc, device=dev, dtype=torch.int32), n_loc
     rows = rows[:n_dirty].sort().values.long()
-    tot = torch.tensor([n_dirty], dtype=torch.int64, device=dev)
+    # the seed anchors of every shard take the same plain path
+    rows = torch.unique(torch.cat([torch.arange(seed[g], device=dev, dtype=torch.int64), rows]))
+    n_plain = int(rows.numel())
+    tot = torch.tensor([n_plain], dtype=torch.int64, device=dev)
     all_n = [torch.zeros_like(tot) for _ in range(G)]
     dist.all_gather(all_n, tot, group=index.group)
     all_n = [int(t.item()) for t in all_n]
     if stats is not None:
-        stats.update(steps=steps, blocks=n_blocks, dirty_rows=n_dirty, dirty_rows_all_ranks=sum(all_n))
+        stats.update(steps=steps, blocks=n_blocks, dirty_rows=n_dirty, seed_rows=seed[g], plain_rows_all_ranks=sum(all_n))
     for owner in range(G):
         src = dist.get_global_rank(index.group, owner) if index.group is not None else owner
         for q0 in range(0, all_n[owner], 65536):

@@ -195,7 +195,12 @@ int cvdb_merge_keys(const uint64_t* keys, int64_t nq, int nlists, int k_in, int 
  *           Chunk sizes should start small and at most double (256, 256, 512, 1024, ...): a row's buffer takes the
  *           candidates of ONE chunk under the threshold of the chunks before it.  id_base is added to every id that
  *           leaves the index (row-direction keys, and the anchors' ids in the column lists): the shard offset
- *   cross   the block (anchors of ANOTHER shard) x (rows [row_begin, row_end) of this index; row_end <= 0: ntotal):
+ *   seed    warms the column side up with plain searches instead of the first (smallest) chunks: the seed anchors
+ *           [0, seed_rows) get their final row-direction result over ALL rows (keys_seed [seed_rows][k], may be NULL
+ *           when the caller computes them elsewhere), and every later row starts its column list with its top-k among
+ *           the seed anchors.  The chunks then start at row seed_rows with chunk sizes from seed_rows up
+ *   cross   the block (anchors of ANOTHER shard) x (rows [row_begin, row_end) of this index; row_end <= 0: ntotal);
+ *           only rows >= col_row_min collect in the column direction:
  *           q [nq][d] are the anchors' vectors, q_ids [nq] their global ids, group_q [nq] their groups (or NULL);
  *           row direction -> keys [nq][k] with ids + id_base, column direction -> the lists of this index's rows.
  *           One of the two shards of a pair computes the block; the other receives the keys (see sharded.py)
@@ -206,8 +211,9 @@ int cvdb_merge_keys(const uint64_t* keys, int64_t nq, int nlists, int k_in, int 
  *   end     frees the join state */
 int cvdb_selfjoin_begin(cvdb_index_t idx, int k, void* stream);
 int cvdb_selfjoin_chunk(cvdb_index_t idx, int64_t row0, int64_t nrows, int64_t id_base, uint64_t* keys, void* stream);
+int cvdb_selfjoin_seed(cvdb_index_t idx, int64_t seed_rows, int64_t id_base, uint64_t* keys_seed, void* stream);
 int cvdb_selfjoin_cross(cvdb_index_t idx, const void* q, int64_t nq, int dtype, const int32_t* q_ids, const int32_t* group_q,
-                        int64_t row_begin, int64_t row_end, int64_t id_base, uint64_t* keys, void* stream);
+                        int64_t row_begin, int64_t row_end, int64_t col_row_min, int64_t id_base, uint64_t* keys, void* stream);
 int cvdb_selfjoin_finish(cvdb_index_t idx, int64_t row0, int64_t nrows, const uint64_t* row_keys, float* D, int64_t* I,
                          void* stream);
 int cvdb_selfjoin_dirty(cvdb_index_t idx, int32_t* rows_out, int64_t max_out, int64_t* n_out, void* stream);

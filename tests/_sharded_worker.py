@@ -58,13 +58,14 @@ def main():
     # sharded SYMMETRIC self-join (every pair of rows scored once in the whole job) == the plain join, on the owner's rows
     from cloudvectordb_b200 import mine_hard_negatives_sharded_symmetric
     st = {}
-    D3, I3 = mine_hard_negatives_sharded_symmetric(shm, emb[lo:hi].to(dev), km_, grp[lo:hi].to(dev), chunk=2048, stats=st)
+    D3, I3 = mine_hard_negatives_sharded_symmetric(shm, emb[lo:hi].to(dev), km_, grp[lo:hi].to(dev), chunk=2048, first_chunk=512,
+                                                   stats=st)
     assert torch.equal(I3, I1[lo:hi]) and torch.allclose(D3, D1[lo:hi], atol=1e-6), f"sharded symmetric join != plain join {st}"
     # uneven shards, no groups, a chunk size that leaves ragged tails
     shu = ShardedIndex(dm, "ip", "bf16", device=local)
     cut = [0] + [int(m * (r + 1) / world) - (37 * (r + 1) if r + 1 < world else 0) for r in range(world)]
     shu.add_local(emb[cut[rank]:cut[rank + 1]].to(dev))
-    D4, I4 = mine_hard_negatives_sharded_symmetric(shu, emb[cut[rank]:cut[rank + 1]].to(dev), km_, None, chunk=1024)
+    D4, I4 = mine_hard_negatives_sharded_symmetric(shu, emb[cut[rank]:cut[rank + 1]].to(dev), km_, None, chunk=1024, first_chunk=256)
     D5, I5 = mine_hard_negatives(emb.to(dev), km_, None, device=local, chunk=4096)
     assert torch.equal(I4, I5[cut[rank]:cut[rank + 1]]), "sharded symmetric join (uneven shards) != plain join"
     # sharded IVF == single-GPU IVF with the same centroids (same lists probed, union of the shards' rows)

@@ -31,27 +31,29 @@ def check(D, I, D_ref, I_ref, tol=2e-5):
 def test_schedule_covers_rows_in_order_and_at_most_doubles():
     from cloudvectordb_b200 import selfjoin_schedule
     for n in (1, 255, 256, 257, 5000, 200_000, 6_250_000):
-        s = selfjoin_schedule(n, 65536)
+        s = selfjoin_schedule(n, 65536, 256 if n < 100_000 else 8192)
         assert s[0][0] == 0 and sum(m for _, m in s) == n
         for (r0, m), (r1, _) in zip(s, s[1:]):
             assert r1 == r0 + m and r0 % 256 == 0 and m <= 65536 and (r0 == 0 or m <= r0)
 
 
-@pytest.mark.parametrize("n,d,k,chunk", [
-    (20_000, 64, 10, 2048),      # many chunks, K <= 512 configuration
-    (9_000, 768, 50, 4096),      # K = 768 configuration (TMEM + shared-memory tail), k = 50
-    (6_001, 96, 100, 65536),     # ragged size, k = 100
-    (3_000, 40, 2, 256),         # smallest k, smallest chunks
-    (700, 32, 20, 65536),        # fewer rows than three chunks
+@pytest.mark.parametrize("n,d,k,chunk,first", [
+    (20_000, 64, 10, 2048, 256),     # many chunks, K <= 512 configuration
+    (9_000, 768, 50, 4096, 512),     # K = 768 configuration (TMEM + shared-memory tail), k = 50
+    (6_001, 96, 100, 65536, 256),    # ragged size, k = 100
+    (3_000, 40, 2, 256, 256),        # smallest k, smallest chunks
+    (700, 32, 20, 65536, 256),       # fewer rows than three chunks
+    (30_000, 64, 10, 8192, 8192),    # the default seed size
+    (5_000, 64, 10, 65536, 8192),    # the seed covers every row: all plain
 ])
-def test_symmetric_join_equals_plain_join_and_oracle(n, d, k, chunk):
+def test_symmetric_join_equals_plain_join_and_oracle(n, d, k, chunk, first):
     from cloudvectordb_b200 import mine_hard_negatives
     rng = np.random.default_rng(n + k)
     emb = O.bf16_round(unit_rows(rng, n, d))
     groups = (np.arange(n) // 4).astype(np.int32)
     groups[::9] = -1                                          # some rows without a group
     D_ref, I_ref = oracle_join(emb, k, groups)
-    D, I = mine_hard_negatives(emb, k, groups, chunk=chunk, symmetric=True)
+    D, I = mine_hard_negatives(emb, k, groups, chunk=chunk, symmetric=True, first_chunk=first)
     check(D, I, D_ref, I_ref)
     assert not np.any(I == np.arange(n)[:, None])
     same = (groups[np.clip(I, 0, None)] == groups[:, None]) & (groups[:, None] >= 0) & (I >= 0)
@@ -69,7 +71,7 @@ def test_ties_between_the_two_directions_go_to_the_lower_id():
     emb = O.bf16_round(unit_rows(rng, n, d))
     dup = [10, 300, 1100, 2500, 4097, 6000, 7999]
     emb[dup] = emb[10]
-    D, I = mine_hard_negatives(emb, k, None, chunk=1024, symmetric=True)
+    D, I = mine_hard_negatives(emb, k, None, chunk=1024, symmetric=True, first_chunk=256)
     D_ref, I_ref = oracle_join(emb, k, None)
     assert np.array_equal(I, I_ref)
     for r in dup:
@@ -92,7 +94,7 @@ def test_adversarial_row_order_overflows_the_column_buffers_and_is_recomputed():
     idx.add(emb)
     idx.set_groups(groups)
     stats = {}
-    D, I = mine_hard_negatives_symmetric(idx, k, emb=emb, groups=groups, chunk=4096, stats=stats)
+    D, I = mine_hard_negatives_symmetric(idx, k, emb=emb, groups=groups, chunk=4096, first_chunk=256, stats=stats)
     idx.close()
     assert stats["dirty_rows"] > 0
     D_ref, I_ref = oracle_join(emb, k, groups)
@@ -133,5 +135,6 @@ def test_selfjoin_argument_checks():
     keys = torch.empty((300, 10), dtype=torch.int64, device="cuda")
     assert lib.cvdb_selfjoin_chunk(idx._h, 64, 100, 0, keys.data_ptr(), None) == _C.EINVAL   # unaligned start
     assert lib.cvdb_selfjoin_chunk(idx._h, 256, 100, 0, keys.data_ptr(), None) == _C.EINVAL  # past the end
+    assert lib.cvdb_selfjoin_seed(idx._h, 100, 0, keys.data_ptr(), None) == _C.EINVAL         # seed not a multiple of 128
     assert lib.cvdb_selfjoin_end(idx._h) == 0
     idx.close()
