@@ -157,7 +157,8 @@ struct Index {
     DevBuf gthr, waves, stage_in, q_pack, q_norm, cand, part, out_d, out_i, ids_a, ids_b, groups;
     // symmetric self-join state (cvdb_selfjoin_*): per database row a threshold, a counter, the survivors' count
     // and a buffer of kColCap keys for the column direction; sj_k > 0 while a join is open
-    DevBuf col_thr, col_cnt, col_base, col_buf, col_dirty, col_scal;
+    DevBuf col_thr, col_cnt, col_base, col_buf, col_dirty, col_scal, col_log;
+    unsigned long long col_log_cap = 0;  // records
     int sj_k = 0;
     DevBuf bad_rows;  // one uint64: rows (added or queried) whose squared norm was not finite
     bool has_groups = false;
@@ -666,9 +667,9 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         const int cfg = p.nkb <= 8 ? 0 : (p.nkb <= 12 ? 1 : 2);  // all of K in TMEM / + 4-block tail / + 5-block tail
         if (ex && ex->col) {
             p.col_thr = ix->col_thr.as<float>();
-            p.col_cnt = ix->col_cnt.as<uint32_t>();
-            p.col_buf = ix->col_buf.as<uint64_t>();
-            p.col_cap = kColCap;
+            p.col_log = ix->col_log.as<uint4>();
+            p.col_log_cnt = ix->col_scal.as<unsigned long long>() + 2;
+            p.col_log_cap = ix->col_log_cap;
             p.col_row_min = static_cast<int>(ex->col_row_min);
             p.q_ids = ex->q_ids;
             LAUNCH(launch_ts2_col(cfg, E, tx, tq, q_rows, ix->row_elems, p, grid, st));
@@ -907,7 +908,8 @@ int cvdb_index_destroy(cvdb_index_t h) {
     for (DevBuf* b : {&ix->row_ids, &ix->list_off, &ix->ivf_cnt, &ix->ivf_pair_off, &ix->ivf_item_off, &ix->ivf_cursor,
                       &ix->ivf_scal, &ix->ivf_items, &ix->ivf_pair_query, &ix->ivf_pair_dst, &ix->ivf_qg, &ix->ivf_probes})
         b->release();
-    for (DevBuf* b : {&ix->col_thr, &ix->col_cnt, &ix->col_base, &ix->col_buf, &ix->col_dirty, &ix->col_scal}) b->release();
+    for (DevBuf* b : {&ix->col_thr, &ix->col_cnt, &ix->col_base, &ix->col_buf, &ix->col_dirty, &ix->col_scal, &ix->col_log})
+        b->release();
     for (DevBuf* b : {&ix->gthr, &ix->waves, &ix->stage_in, &ix->q_pack, &ix->q_norm, &ix->cand, &ix->part, &ix->out_d, &ix->out_i, &ix->ids_a,
                       &ix->ids_b, &ix->groups, &ix->bad_rows})
         b->release();
@@ -1397,8 +1399,13 @@ int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
     TRY(ix->col_cnt.ensure(n * 4));
     TRY(ix->col_base.ensure(n * 4));
     TRY(ix->col_dirty.ensure(n));
-    TRY(ix->col_scal.ensure(16));
+    TRY(ix->col_scal.ensure(32));  // [0] dirty-row count, [1] log overflow flag, [2] log cursor
     TRY(ix->col_buf.ensure(n * kColCap * 8));
+    // the log takes the column candidates of ONE launch: about k per collecting row while chunks at most double
+    ix->col_log_cap = std::max<unsigned long long>(1ull << 22, 2ull * n * static_cast<unsigned long long>(k));
+    TRY(ix->col_log.ensure(ix->col_log_cap * 16));
+    CU_TRY(cudaMemsetAsync(ix->col_log.p, 0, ix->col_log_cap * 16, st));
+    CU_TRY(cudaMemsetAsync(ix->col_scal.p, 0, 32, st));
     CU_TRY(cudaMemsetAsync(ix->col_cnt.p, 0, n * 4, st));
     CU_TRY(cudaMemsetAsync(ix->col_base.p, 0, n * 4, st));
     CU_TRY(cudaMemsetAsync(ix->col_dirty.p, 0, n, st));
@@ -1411,6 +1418,13 @@ int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
 
 namespace {
 int selfjoin_compact(Index* ix, int64_t row_min, int64_t row_end, cudaStream_t st) {
+    // the launch's log of column candidates -> the rows' buffers
+    col_scatter_kernel<<<148 * 16, 256, 0, st>>>(ix->col_log.as<uint4>(), ix->col_scal.as<unsigned long long>() + 2,
+                                                 ix->col_log_cap, ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>());
+    col_log_reset_kernel<<<1, 32, 0, st>>>(ix->col_scal.as<unsigned long long>() + 2, ix->col_log_cap,
+                                           ix->col_scal.as<unsigned long long>() + 1);
+    g_launches += 2;
+    CU_TRY(cudaGetLastError());
     if (row_min >= row_end) return CVDB_OK;
     const int64_t blocks = std::min<int64_t>(ceil_div(row_end - row_min, 8), 148 * 32);
     col_compact_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
@@ -1560,10 +1574,11 @@ int cvdb_selfjoin_dirty(cvdb_index_t h, int32_t* rows_out, int64_t max_out, int6
     collect_flagged_kernel<<<static_cast<unsigned>(ceil_div(ix->ntotal, 256)), 256, 0, st>>>(
         ix->col_dirty.as<uint8_t>(), ix->ntotal, rows_out, max_out, ix->col_scal.as<unsigned long long>());
     ++g_launches;
-    unsigned long long c = 0;
-    CU_TRY(cudaMemcpyAsync(&c, ix->col_scal.p, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long c[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(c, ix->col_scal.p, 16, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    *n_out = static_cast<int64_t>(c);
+    // a log that ran over its capacity lost candidates of unknown rows: every row has to be recomputed
+    *n_out = c[1] ? std::max<int64_t>(ix->ntotal, max_out + 1) : static_cast<int64_t>(c[0]);
     return CVDB_OK;
 }
 
@@ -1573,7 +1588,7 @@ int cvdb_selfjoin_end(cvdb_index_t h) {
     cvdb_guard g(ix->device);
     cudaDeviceSynchronize();
     ix->sj_k = 0;
-    for (DevBuf* b : {&ix->col_thr, &ix->col_cnt, &ix->col_base, &ix->col_buf, &ix->col_dirty}) b->release();
+    for (DevBuf* b : {&ix->col_thr, &ix->col_cnt, &ix->col_base, &ix->col_buf, &ix->col_dirty, &ix->col_log}) b->release();
     return CVDB_OK;
 }
 

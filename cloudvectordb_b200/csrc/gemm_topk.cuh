@@ -258,7 +258,7 @@ __device__ __forceinline__ void make_room(LaneTopk<E>& st, int k, int room, cons
 template <int E>
 __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[32], uint32_t row0, uint32_t row_end,
                                            uint32_t self, int grp, const int32_t* __restrict__ group_db, int k, int room,
-                                           float* m_out = nullptr) {
+                                           float* m8_out = nullptr) {
     float m8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -268,7 +268,9 @@ __device__ __forceinline__ void scan_chunk(LaneTopk<E>& st, const uint32_t (&v)[
         m8[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
     }
     const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-    if (m_out != nullptr) *m_out = m;  // the column direction of the symmetric join tests the same maximum
+    if (m8_out != nullptr) {  // the column direction of the symmetric join tests the same maxima
+        m8_out[0] = m8[0]; m8_out[1] = m8[1]; m8_out[2] = m8[2]; m8_out[3] = m8[3];
+    }
     if (!__any_sync(0xffffffffu, m > st.thr)) return;  // common case once the threshold has settled
     if constexpr (E >= 2) {
         // Buffers of 64+ slots: make room for a whole chunk (32 candidates) once, then let only the lanes that
@@ -953,34 +955,61 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // COLUMN DIRECTION (symmetric self-join).  When the queries are rows of the database itself, the score of
 // (query i, row j) is also the score of (query j, row i): a tile computed once can feed the top-k of its query
 // rows (the usual row-wise filter) AND the top-k of its database rows, with the query as the candidate.  The
-// column side keeps its state in global memory, one threshold / counter / key buffer per database row
-// (GemmTopkParams::col_*): thresholds are read once per tile (lane l holds the columns l, l+32, ...), a chunk of 32
-// columns is skipped when no score of the warp beats the smallest of its 32 thresholds, and a candidate claims
-// a slot with an atomicAdd on the row's counter.  Buffers are compacted between launches (col_compact_kernel):
-// a row that ran over its buffer is flagged and recomputed exactly by the caller.
+// column side keeps its state in global memory, one threshold / counter / key buffer per database row: thresholds
+// (GemmTopkParams::col_thr) are read once per tile, one tile ahead (lane l holds the columns l, l+32, ...); a chunk
+// of 32 columns is skipped when no score of the warp beats the smallest of its 32 thresholds, a group of 8 when
+// none beats the smallest of its 8; a candidate is appended to a log that col_scatter_kernel distributes to the
+// rows' buffers after the launch.  Buffers are compacted between launches (col_compact_kernel): a row that ran over
+// its buffer is flagged and recomputed exactly by the caller.
 // ===========================================================================
 // anchor_id: the query's id in the id space of the column lists (a global id when the database is one shard of
 // many); self_row: the database row that IS the query (none: 0xFFFFFFFF); grp: the query's group (< 0: none) -- a
 // row of the same group is not offered the query (checked here, per candidate: the claim of a slot is a global
 // round trip anyway).
-__device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], float m, float cthr_lane, float cmin, uint32_t row0,
+// A candidate is not written into its row's buffer here (claiming a slot needs the atomic's return value: one
+// global round trip per candidate, ~2.5 us per slow chunk in the first version) but appended to a LOG: every
+// thread owns segments of 8 records in a global array, reserved 8 at a time with one atomicAdd, and just stores
+// (row, key) at its cursor.  col_scatter_kernel distributes the log to the rows after the launch, with all the
+// parallelism of a plain kernel to hide the atomics.
+struct ColLogCursor {
+    unsigned long long cur = 0, end = 0;
+};
+constexpr int kColLogSeg = 8;
+__device__ __forceinline__ void col_log_push(ColLogCursor& lc, const GemmTopkParams& p, uint32_t row, uint64_t key) {
+    if (lc.cur == lc.end) {
+        lc.cur = atomicAdd(p.col_log_cnt, static_cast<unsigned long long>(kColLogSeg));
+        lc.end = lc.cur + kColLogSeg;
+    }
+    if (lc.cur < p.col_log_cap)  // past the end: dropped; the host sees the counter and falls back
+        p.col_log[lc.cur] = make_uint4(row, 0u, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+    ++lc.cur;
+}
+
+__device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], const float (&m8)[4], float cthr_lane, uint32_t row0,
                                                uint32_t anchor_id, uint32_t self_row, int grp, bool q_valid,
-                                               const GemmTopkParams& p) {
-    if (!__any_sync(0xffffffffu, q_valid && m > cmin)) return;
+                                               const GemmTopkParams& p, ColLogCursor& lc) {
+    // gmin[g]: the smallest threshold among the chunk's columns 8g .. 8g+7 (lane l holds column l's threshold)
+    float gm = cthr_lane;
+    gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, 1));
+    gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
+    gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, 4));
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float tj = __shfl_sync(0xffffffffu, cthr_lane, j);  // +inf for rows that do not collect
-        const float s = __uint_as_float(v[j]);
-        if (q_valid && s > tj) {
-            const uint32_t row = row0 + j;
-            if (row != self_row && !(grp >= 0 && p.group_db != nullptr && __ldg(p.group_db + row) == grp)) {
-                const uint32_t pos = atomicAdd(p.col_cnt + row, 1u);
-                if (pos < static_cast<uint32_t>(p.col_cap))
-                    p.col_buf[static_cast<size_t>(row) * p.col_cap + pos] = make_key(s, anchor_id);
+    for (int g = 0; g < 4; ++g) {
+        const float gmin = __shfl_sync(0xffffffffu, gm, 8 * g);
+        if (!__any_sync(0xffffffffu, q_valid && m8[g] > gmin)) continue;  // nobody beats any column of the group
+#pragma unroll
+        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+            const float tj = __shfl_sync(0xffffffffu, cthr_lane, j);  // +inf for rows that do not collect
+            const float s = __uint_as_float(v[j]);
+            if (q_valid && s > tj) {
+                const uint32_t row = row0 + j;
+                if (row != self_row && !(grp >= 0 && p.group_db != nullptr && __ldg(p.group_db + row) == grp))
+                    col_log_push(lc, p, row, make_key(s, anchor_id));
             }
         }
     }
 }
+
 // ===========================================================================
 // CTA pair (cta_group::2, M = 256) with the QUERIES RESIDENT ON CHIP.
 //
@@ -1206,6 +1235,7 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         uint32_t acc_phase = 0;
         const int dbg = p.dbg;
         LaneTopk<E> st;
+        ColLogCursor col_log;  // (column direction only)
         if constexpr (E > 0)
             st.buf = p.cand + (static_cast<size_t>(blockIdx.x) * 128 + ewarp * 32 + lane) * C;
         for (int w = pair; w < n_items; w += n_pairs) {
@@ -1245,17 +1275,25 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             if constexpr (COL) {
                 if (p.q_ids != nullptr && q_valid) anchor_id = static_cast<uint32_t>(__ldg(p.q_ids + q_row));
             }
+            // column direction: the thresholds of a tile's database rows (lane l: columns l, l+32, ...), fetched one
+            // tile ahead so the L2 round trip never sits between an accumulator becoming ready and its scan
+            float cthr_next[COL ? BLOCK_N / 32 : 1];
+            auto load_cthr = [&](int t, float (&out)[COL ? BLOCK_N / 32 : 1]) {
+#pragma unroll
+                for (int c = 0; c < (COL ? BLOCK_N / 32 : 1); ++c) {
+                    const uint32_t r = static_cast<uint32_t>(t) * BLOCK_N + c * 32 + lane;
+                    out[c] = (r >= static_cast<uint32_t>(p.col_row_min) && r < static_cast<uint32_t>(p.n_rows))
+                                 ? __ldcg(p.col_thr + r) : INFINITY;
+                }
+            };
+            if constexpr (COL) load_cthr(t0, cthr_next);
             for (int t = t0; t < t1; ++t) {
                 const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
-                // column direction: the thresholds of the tile's database rows, fetched while the MMA still runs
                 float cthr[COL ? BLOCK_N / 32 : 1], cmin[COL ? BLOCK_N / 32 : 1];
                 if constexpr (COL) {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
-                        const uint32_t r = row0 + c * 32 + lane;
-                        cthr[c] = (r >= static_cast<uint32_t>(p.col_row_min) && r < static_cast<uint32_t>(p.n_rows))
-                                      ? __ldcg(p.col_thr + r) : INFINITY;
-                    }
+                    for (int c = 0; c < BLOCK_N / 32; ++c) cthr[c] = cthr_next[c];
+                    if (t + 1 < t1) load_cthr(t + 1, cthr_next);
 #pragma unroll
                     for (int c = 0; c < BLOCK_N / 32; ++c) {
                         float mn = cthr[c];
@@ -1279,17 +1317,19 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
                     }
-                    float m_chunk = -INFINITY;
+                    float m8c[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                     if (!(dbg & 3))
                         scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room,
-                                      COL ? &m_chunk : nullptr);
+                                      COL ? m8c : nullptr);
                     if constexpr (COL) {
                         float ct = cthr[0], cm = cmin[0];  // (the loop is not unrolled: pick the chunk's registers)
 #pragma unroll
                         for (int q = 1; q < BLOCK_N / 32; ++q)
                             if (c == q * 32) { ct = cthr[q]; cm = cmin[q]; }
-                        if (cm < INFINITY)  // warp-uniform: some row of the chunk collects
-                            scan_chunk_col(v, m_chunk, ct, cm, row0 + c, anchor_id, self, grp, q_valid, p);
+                        const float m_chunk = fmaxf(fmaxf(m8c[0], m8c[1]), fmaxf(m8c[2], m8c[3]));
+                        // cm is warp-uniform; +inf: no row of the chunk collects
+                        if (cm < INFINITY && __any_sync(0xffffffffu, q_valid && m_chunk > cm))
+                            scan_chunk_col(v, m8c, ct, row0 + c, anchor_id, self, grp, q_valid, p, col_log);
                     }
                 }
                 acc ^= 1;

@@ -1,6 +1,7 @@
 // Parameter blocks of the GEMM+top-k kernels (plain data, shared by the kernels and the C ABI).
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace cvdb {
 
@@ -33,9 +34,9 @@ struct GemmTopkParams {
     int tile0;       // first database tile of the launch (n_tiles stays the END tile; rows before tile0 are not scanned)
     // column direction of a symmetric self-join (gemm_topk.cuh, scan_chunk_col); col_thr == null: off
     const float* col_thr;  // [n_rows] a score must beat it to become a candidate of that database row
-    uint32_t* col_cnt;     // [n_rows] slots claimed in the row's buffer (may run past col_cap: the row overflowed)
-    uint64_t* col_buf;     // [n_rows][col_cap] keys (score, ~query id)
-    int col_cap;
+    uint4* col_log;                      // append-only log of column candidates {row, 0, key lo, key hi}
+    unsigned long long* col_log_cnt;     // records reserved so far (in segments of 8)
+    unsigned long long col_log_cap;      // capacity of the log in records
     int col_row_min;       // database rows below this do not collect
     const int32_t* q_ids;  // [nq] id of query i in the id space of the column lists (null: self_ids[i])
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
