@@ -562,20 +562,22 @@ __global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __r
 }
 
 // Distribute the log of column candidates (gemm_topk.cuh, col_log_push) to the rows' buffers: one thread per record,
-// slot from an atomicAdd on the row's counter (a counter past kColCap marks the row as overflowed); consumed
+// same-group candidates dropped, slot from an atomicAdd on the row's counter (a counter past kColCap marks the row as overflowed); consumed
 // records are zeroed so that the unused tail of a thread's last segment reads as empty next time.
 __global__ void col_scatter_kernel(uint4* __restrict__ log, const unsigned long long* __restrict__ log_cnt,
                                    unsigned long long log_cap, uint64_t* __restrict__ col_buf,
-                                   uint32_t* __restrict__ col_cnt) {
+                                   uint32_t* __restrict__ col_cnt, const int32_t* __restrict__ group_db) {
     const unsigned long long n = min(*log_cnt, log_cap);
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint4 r = log[i];
         const uint64_t key = (static_cast<uint64_t>(r.w) << 32) | r.z;
         if (key == 0) continue;
+        log[i] = make_uint4(0u, 0u, 0u, 0u);
+        // record = {row, the candidate's group, key}: a row does not take a candidate of its own group
+        if (group_db != nullptr && static_cast<int>(r.y) >= 0 && group_db[r.x] == static_cast<int>(r.y)) continue;
         const uint32_t pos = atomicAdd(col_cnt + r.x, 1u);
         if (pos < static_cast<uint32_t>(kColCap)) col_buf[static_cast<size_t>(r.x) * kColCap + pos] = key;
-        log[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 // after the scatter: a log that ran over its capacity lost candidates (overflow[0] = 1); the counter restarts

@@ -1420,7 +1420,8 @@ namespace {
 int selfjoin_compact(Index* ix, int64_t row_min, int64_t row_end, cudaStream_t st) {
     // the launch's log of column candidates -> the rows' buffers
     col_scatter_kernel<<<148 * 16, 256, 0, st>>>(ix->col_log.as<uint4>(), ix->col_scal.as<unsigned long long>() + 2,
-                                                 ix->col_log_cap, ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>());
+                                                 ix->col_log_cap, ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
+                                                 ix->has_groups ? ix->groups.as<int32_t>() : nullptr);
     col_log_reset_kernel<<<1, 32, 0, st>>>(ix->col_scal.as<unsigned long long>() + 2, ix->col_log_cap,
                                            ix->col_scal.as<unsigned long long>() + 1);
     g_launches += 2;

@@ -963,9 +963,8 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // its buffer is flagged and recomputed exactly by the caller.
 // ===========================================================================
 // anchor_id: the query's id in the id space of the column lists (a global id when the database is one shard of
-// many); self_row: the database row that IS the query (none: 0xFFFFFFFF); grp: the query's group (< 0: none) -- a
-// row of the same group is not offered the query (checked here, per candidate: the claim of a slot is a global
-// round trip anyway).
+// many); self_row: the database row that IS the query (none: 0xFFFFFFFF); grp: the query's group (< 0: none),
+// recorded with the candidate.
 // A candidate is not written into its row's buffer here (claiming a slot needs the atomic's return value: one
 // global round trip per candidate, ~2.5 us per slow chunk in the first version) but appended to a LOG: every
 // thread owns segments of 8 records in a global array, reserved 8 at a time with one atomicAdd, and just stores
@@ -975,13 +974,13 @@ struct ColLogCursor {
     unsigned long long cur = 0, end = 0;
 };
 constexpr int kColLogSeg = 8;
-__device__ __forceinline__ void col_log_push(ColLogCursor& lc, const GemmTopkParams& p, uint32_t row, uint64_t key) {
+__device__ __forceinline__ void col_log_push(ColLogCursor& lc, const GemmTopkParams& p, uint32_t row, int grp, uint64_t key) {
     if (lc.cur == lc.end) {
         lc.cur = atomicAdd(p.col_log_cnt, static_cast<unsigned long long>(kColLogSeg));
         lc.end = lc.cur + kColLogSeg;
     }
     if (lc.cur < p.col_log_cap)  // past the end: dropped; the host sees the counter and falls back
-        p.col_log[lc.cur] = make_uint4(row, 0u, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+        p.col_log[lc.cur] = make_uint4(row, static_cast<uint32_t>(grp), static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
     ++lc.cur;
 }
 
@@ -1003,8 +1002,9 @@ __device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], const fl
             const float s = __uint_as_float(v[j]);
             if (q_valid && s > tj) {
                 const uint32_t row = row0 + j;
-                if (row != self_row && !(grp >= 0 && p.group_db != nullptr && __ldg(p.group_db + row) == grp))
-                    col_log_push(lc, p, row, make_key(s, anchor_id));
+                // (a row of the query's own group is refused by col_scatter_kernel: the group lookup is an L2 round
+                // trip that would stall the warp here)
+                if (row != self_row) col_log_push(lc, p, row, grp, make_key(s, anchor_id));
             }
         }
     }
@@ -1289,18 +1289,18 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             if constexpr (COL) load_cthr(t0, cthr_next);
             for (int t = t0; t < t1; ++t) {
                 const uint32_t row0 = static_cast<uint32_t>(t) * BLOCK_N;
-                float cthr[COL ? BLOCK_N / 32 : 1], cmin[COL ? BLOCK_N / 32 : 1];
+                float cthr[COL ? BLOCK_N / 32 : 1];
+                float cmin_tile = INFINITY;  // the smallest threshold among the tile's columns (+inf: nobody collects)
                 if constexpr (COL) {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N / 32; ++c) cthr[c] = cthr_next[c];
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        cthr[c] = cthr_next[c];
+                        cmin_tile = fminf(cmin_tile, cthr[c]);
+                    }
                     if (t + 1 < t1) load_cthr(t + 1, cthr_next);
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
-                        float mn = cthr[c];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                        cmin[c] = mn;
-                    }
+                    for (int o = 16; o > 0; o >>= 1) cmin_tile = fminf(cmin_tile, __shfl_xor_sync(0xffffffffu, cmin_tile, o));
+                    if (!q_valid) cmin_tile = INFINITY;  // padding query rows never offer themselves
                 }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -1322,14 +1322,15 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         scan_chunk<E>(st, v, row0 + c, static_cast<uint32_t>(p.n_rows), self, grp, p.group_db, p.k, p.room,
                                       COL ? m8c : nullptr);
                     if constexpr (COL) {
-                        float ct = cthr[0], cm = cmin[0];  // (the loop is not unrolled: pick the chunk's registers)
-#pragma unroll
-                        for (int q = 1; q < BLOCK_N / 32; ++q)
-                            if (c == q * 32) { ct = cthr[q]; cm = cmin[q]; }
+                        // fast path: one compare against the tile's smallest threshold and one vote per chunk
                         const float m_chunk = fmaxf(fmaxf(m8c[0], m8c[1]), fmaxf(m8c[2], m8c[3]));
-                        // cm is warp-uniform; +inf: no row of the chunk collects
-                        if (cm < INFINITY && __any_sync(0xffffffffu, q_valid && m_chunk > cm))
+                        if (__any_sync(0xffffffffu, m_chunk > cmin_tile)) {
+                            float ct = cthr[0];  // (the loop is not unrolled: pick the chunk's register)
+#pragma unroll
+                            for (int q = 1; q < BLOCK_N / 32; ++q)
+                                if (c == q * 32) ct = cthr[q];
                             scan_chunk_col(v, m8c, ct, row0 + c, anchor_id, self, grp, q_valid, p, col_log);
+                        }
                     }
                 }
                 acc ^= 1;

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=50)
     ap.add_argument("--skip-plain", action="store_true")
+    ap.add_argument("--first", default="8192", help="comma list of seed sizes to try")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "selfjoin.jsonl"))
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -45,12 +46,19 @@ def main():
     mine_hard_negatives(emb[:70_000], a.k, groups[:70_000], index=small)
     small.close()
     torch.cuda.synchronize()
-    stats = {}
-    t0 = time.perf_counter()
-    Ds, Is = mine_hard_negatives_symmetric(idx, a.k, emb=emb, groups=groups, stats=stats)
-    torch.cuda.synchronize()
-    ts = time.perf_counter() - t0
-    rec.update(symmetric_s=ts, symmetric_tflops_on_full_count=flops / ts / 1e12, symmetric_stats=stats)
+    best = None
+    for first in [int(v) for v in a.first.split(",")]:
+        stats = {}
+        t0 = time.perf_counter()
+        Ds, Is = mine_hard_negatives_symmetric(idx, a.k, emb=emb, groups=groups, first_chunk=first, stats=stats)
+        torch.cuda.synchronize()
+        ts_ = time.perf_counter() - t0
+        rec[f"symmetric_s_first{first}"] = ts_
+        rec[f"symmetric_stats_first{first}"] = stats
+        if best is None or ts_ < best:
+            best = ts_
+    ts = best
+    rec.update(symmetric_s=ts, symmetric_tflops_on_full_count=flops / ts / 1e12)
     if not a.skip_plain:
         t0 = time.perf_counter()
         Dp, Ip = mine_hard_negatives(emb, a.k, groups, index=idx)
