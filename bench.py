@@ -61,7 +61,8 @@ def parse():
     ap.add_argument("--configs", default="all", help="all | none | comma list of 0,2,3,4,ingest")
     ap.add_argument("--km-points", type=int, default=100_000_000, help="configs[3]: points in total (split over the ranks)")
     ap.add_argument("--lat-rows", type=int, default=12_500_000, help="configs[4]: database rows PER rank")
-    ap.add_argument("--sj-rows", type=int, default=1_000_000, help="configs[2] whole self-join: rows PER rank")
+    ap.add_argument("--sj-rows", type=int, default=0,
+                    help="configs[2] whole self-join: rows PER rank (default: 2M on one GPU, 1M per rank otherwise)")
     ap.add_argument("--dbg", type=int, default=0, help="kernel debug flags (tuning experiments)")
     ap.add_argument("--slices", type=int, default=0, help="override the database-slice heuristic")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 streaming kernel, 2 CTA-pair/TMEM kernel")
@@ -499,7 +500,7 @@ def run_ours(a):
         from cloudvectordb_b200 import (mine_hard_negatives, mine_hard_negatives_sharded,
                                         mine_hard_negatives_sharded_symmetric, mine_hard_negatives_symmetric)
         k = 50
-        n_loc = min(a.sj_rows, hi - lo)
+        n_loc = min(a.sj_rows or (2_000_000 if world == 1 else 1_000_000), hi - lo)
         emb = xb[:n_loc]
         if world > 1:
             sj = ShardedIndex(a.dim, "ip", "bf16", device=local_rank)
@@ -553,7 +554,8 @@ def run_ours(a):
                              "note": "the symmetric join issues half of these flops (SURVEY.md 8(d): 'would show as > 1x on this "
                                      "count'); plain join on the same count: %.1f TFLOP/s per GPU" % (flops / tp / 1e12 / world)},
                 "whole_50M_join_estimate_s_on_8_gpus": ts * (50_000_000 / n_tot) ** 2 * (world / 8.0),
-                "estimate_note": "symmetric_s scaled by (50M / rows_total)^2 and by n_gpus / 8"}
+                "estimate_note": "symmetric_s scaled by (50M / rows_total)^2 and by n_gpus / 8; conservative: the column side costs "
+                                 "about k*log2(rows) candidates per row, so its share of the time shrinks as the corpus grows"}
 
     def cfg_latency():
         """configs[4]: small-batch latency against lat_rows rows PER rank (100M x 768 over 8 GPUs = 12.5M each):
