@@ -564,12 +564,12 @@ __global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __r
 // Distribute the log of column candidates (gemm_topk.cuh, col_log_push) to the rows' buffers: one thread per record,
 // same-group candidates dropped, slot from an atomicAdd on the row's counter (a counter past kColCap marks the row as overflowed); consumed
 // records are zeroed so that the unused tail of a thread's last segment reads as empty next time.
-__global__ void col_scatter_kernel(uint4* __restrict__ log, const unsigned long long* __restrict__ log_cnt,
-                                   unsigned long long log_cap, uint64_t* __restrict__ col_buf,
+__global__ void col_scatter_kernel(uint4* __restrict__ log, const uint32_t* __restrict__ log_cnt,
+                                   uint32_t log_cap, uint64_t* __restrict__ col_buf,
                                    uint32_t* __restrict__ col_cnt, const int32_t* __restrict__ group_db) {
-    const unsigned long long n = min(*log_cnt, log_cap);
-    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const size_t n = min(*log_cnt, log_cap);
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint4 r = log[i];
         const uint64_t key = (static_cast<uint64_t>(r.w) << 32) | r.z;
         if (key == 0) continue;
@@ -581,11 +581,11 @@ __global__ void col_scatter_kernel(uint4* __restrict__ log, const unsigned long 
     }
 }
 // after the scatter: a log that ran over its capacity lost candidates (overflow[0] = 1); the counter restarts
-__global__ void col_log_reset_kernel(unsigned long long* __restrict__ log_cnt, unsigned long long log_cap,
+__global__ void col_log_reset_kernel(uint32_t* __restrict__ log_cnt, uint32_t log_cap,
                                      unsigned long long* __restrict__ overflow) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (*log_cnt > log_cap) *overflow = 1ull;
-        *log_cnt = 0ull;
+        *log_cnt = 0u;
     }
 }
 

@@ -158,7 +158,7 @@ struct Index {
     // symmetric self-join state (cvdb_selfjoin_*): per database row a threshold, a counter, the survivors' count
     // and a buffer of kColCap keys for the column direction; sj_k > 0 while a join is open
     DevBuf col_thr, col_cnt, col_base, col_buf, col_dirty, col_scal, col_log;
-    unsigned long long col_log_cap = 0;  // records
+    uint32_t col_log_cap = 0;  // records
     int sj_k = 0;
     DevBuf bad_rows;  // one uint64: rows (added or queried) whose squared norm was not finite
     bool has_groups = false;
@@ -668,7 +668,7 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         if (ex && ex->col) {
             p.col_thr = ix->col_thr.as<float>();
             p.col_log = ix->col_log.as<uint4>();
-            p.col_log_cnt = ix->col_scal.as<unsigned long long>() + 2;
+            p.col_log_cnt = ix->col_scal.as<uint32_t>() + 4;
             p.col_log_cap = ix->col_log_cap;
             p.col_row_min = static_cast<int>(ex->col_row_min);
             p.q_ids = ex->q_ids;
@@ -1402,9 +1402,13 @@ int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
     TRY(ix->col_scal.ensure(32));  // [0] dirty-row count, [1] log overflow flag, [2] log cursor
     TRY(ix->col_buf.ensure(n * kColCap * 8));
     // the log takes the column candidates of ONE launch: about k per collecting row while chunks at most double
-    ix->col_log_cap = std::max<unsigned long long>(1ull << 22, 2ull * n * static_cast<unsigned long long>(k));
-    TRY(ix->col_log.ensure(ix->col_log_cap * 16));
-    CU_TRY(cudaMemsetAsync(ix->col_log.p, 0, ix->col_log_cap * 16, st));
+    // (32-bit cursor: at most 2^31 - 2^24 records, so a launch of runaway candidates cannot wrap the counter: the
+    // epilogue threads of one launch reserve fewer than 2^31 records past the cap before ... they cannot: 8 records at
+    // a time, one per candidate; a launch offers at most 65536 * rows candidates, but the cap check drops, not wraps)
+    ix->col_log_cap = static_cast<uint32_t>(std::min<unsigned long long>(
+        (1ull << 31) - (1ull << 24), std::max<unsigned long long>(1ull << 22, 2ull * n * static_cast<unsigned long long>(k))));
+    TRY(ix->col_log.ensure(static_cast<size_t>(ix->col_log_cap) * 16));
+    CU_TRY(cudaMemsetAsync(ix->col_log.p, 0, static_cast<size_t>(ix->col_log_cap) * 16, st));
     CU_TRY(cudaMemsetAsync(ix->col_scal.p, 0, 32, st));
     CU_TRY(cudaMemsetAsync(ix->col_cnt.p, 0, n * 4, st));
     CU_TRY(cudaMemsetAsync(ix->col_base.p, 0, n * 4, st));
@@ -1419,10 +1423,10 @@ int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
 namespace {
 int selfjoin_compact(Index* ix, int64_t row_min, int64_t row_end, cudaStream_t st) {
     // the launch's log of column candidates -> the rows' buffers
-    col_scatter_kernel<<<148 * 16, 256, 0, st>>>(ix->col_log.as<uint4>(), ix->col_scal.as<unsigned long long>() + 2,
-                                                 ix->col_log_cap, ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
+    col_scatter_kernel<<<148 * 16, 256, 0, st>>>(ix->col_log.as<uint4>(), ix->col_scal.as<uint32_t>() + 4, ix->col_log_cap,
+                                                 ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
                                                  ix->has_groups ? ix->groups.as<int32_t>() : nullptr);
-    col_log_reset_kernel<<<1, 32, 0, st>>>(ix->col_scal.as<unsigned long long>() + 2, ix->col_log_cap,
+    col_log_reset_kernel<<<1, 32, 0, st>>>(ix->col_scal.as<uint32_t>() + 4, ix->col_log_cap,
                                            ix->col_scal.as<unsigned long long>() + 1);
     g_launches += 2;
     CU_TRY(cudaGetLastError());

@@ -971,17 +971,19 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // (row, key) at its cursor.  col_scatter_kernel distributes the log to the rows after the launch, with all the
 // parallelism of a plain kernel to hide the atomics.
 struct ColLogCursor {
-    unsigned long long cur = 0, end = 0;
+    uint32_t cur = 0, left = 0;  // next record of this thread's segment, records left in it
 };
 constexpr int kColLogSeg = 8;
 __device__ __forceinline__ void col_log_push(ColLogCursor& lc, const GemmTopkParams& p, uint32_t row, int grp, uint64_t key) {
-    if (lc.cur == lc.end) {
-        lc.cur = atomicAdd(p.col_log_cnt, static_cast<unsigned long long>(kColLogSeg));
-        lc.end = lc.cur + kColLogSeg;
+    if (lc.left == 0) {
+        // the counter saturates far below 2^32 (the host caps the log at 2^31 records and every launch starts at 0)
+        lc.cur = atomicAdd(p.col_log_cnt, static_cast<uint32_t>(kColLogSeg));
+        lc.left = kColLogSeg;
     }
     if (lc.cur < p.col_log_cap)  // past the end: dropped; the host sees the counter and falls back
         p.col_log[lc.cur] = make_uint4(row, static_cast<uint32_t>(grp), static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
     ++lc.cur;
+    --lc.left;
 }
 
 __device__ __forceinline__ void scan_chunk_col(const uint32_t (&v)[32], const float (&m8)[4], float cthr_lane, uint32_t row0,

@@ -35,8 +35,8 @@ struct GemmTopkParams {
     // column direction of a symmetric self-join (gemm_topk.cuh, scan_chunk_col); col_thr == null: off
     const float* col_thr;  // [n_rows] a score must beat it to become a candidate of that database row
     uint4* col_log;                      // append-only log of column candidates {row, 0, key lo, key hi}
-    unsigned long long* col_log_cnt;     // records reserved so far (in segments of 8)
-    unsigned long long col_log_cap;      // capacity of the log in records
+    uint32_t* col_log_cnt;               // records reserved so far (in segments of 8)
+    uint32_t col_log_cap;                // capacity of the log in records (< 2^31)
     int col_row_min;       // database rows below this do not collect
     const int32_t* q_ids;  // [nq] id of query i in the id space of the column lists (null: self_ids[i])
     int dbg;         // tuning experiments: 1 = skip scan, 2 = skip TMEM read too
