@@ -500,7 +500,7 @@ def run_ours(a):
         from cloudvectordb_b200 import (mine_hard_negatives, mine_hard_negatives_sharded,
                                         mine_hard_negatives_sharded_symmetric, mine_hard_negatives_symmetric)
         k = 50
-        n_loc = min(a.sj_rows or (2_000_000 if world == 1 else 1_000_000), hi - lo)
+        n_loc = min(a.sj_rows or (6_250_000 if world == 1 else 1_000_000), hi - lo)
         emb = xb[:n_loc]
         if world > 1:
             sj = ShardedIndex(a.dim, "ip", "bf16", device=local_rank)

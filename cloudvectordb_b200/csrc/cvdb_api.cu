@@ -469,7 +469,12 @@ int compaction_trigger(int k, int C) {
 // Split the database into slices so that (query tiles x slices) fills the grid
 // in whole waves.  Cost model: waves * (tiles per slice + fixed per-item overhead).
 void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& n_slices, int& tps, int ovh = 4) {
-    int64_t best = INT64_MAX;
+    // cost of a plan in tile times: waves * (tiles per slice + per-item overhead), plus a penalty for LONG slices.  The
+    // CTAs of a wave stream the same slice and meet again only at the item boundary; over thousands of tiles they
+    // drift further apart than the L2 bridges and re-read the slice from HBM (which costs clock under the power cap).
+    // Measured on the mining chunk (65 536 anchors x 10M rows, k = 50, tools/mining_slices_probe.py): 6010 tiles per
+    // slice 755 ms, 3907: 680, 3005: 665, 2112: 659, 1954: 662 -- i.e. +0.9 / +3 / +14 % at 3000 / 3900 / 6000 tiles.
+    double best = 1e300;
     n_slices = 1;
     tps = n_tiles;
     const int64_t s_max = std::min<int64_t>(std::min<int64_t>(n_tiles, 8LL * grid), std::max<int64_t>(max_slices, 1));
@@ -478,7 +483,8 @@ void choose_slices(int q_tiles, int n_tiles, int grid, int64_t max_slices, int& 
         const int64_t se = ceil_div(n_tiles, t);
         const int64_t items = se * q_tiles;
         const int64_t waves = ceil_div(items, grid);
-        const int64_t cost = waves * (t + ovh);
+        const double over = t > 2000 ? (static_cast<double>(t) - 2000.0) / 1000.0 : 0.0;
+        const double cost = static_cast<double>(waves * (t + ovh)) * (1.0 + 0.009 * over * over);
         if (cost < best) {
             best = cost;
             n_slices = static_cast<int>(se);
@@ -1401,10 +1407,10 @@ int cvdb_selfjoin_begin(cvdb_index_t h, int k, void* stream) {
     TRY(ix->col_dirty.ensure(n));
     TRY(ix->col_scal.ensure(32));  // [0] dirty-row count, [1] log overflow flag, [2] log cursor
     TRY(ix->col_buf.ensure(n * kColCap * 8));
-    // the log takes the column candidates of ONE launch: about k per collecting row while chunks at most double
-    // (32-bit cursor: at most 2^31 - 2^24 records, so a launch of runaway candidates cannot wrap the counter: the
-    // epilogue threads of one launch reserve fewer than 2^31 records past the cap before ... they cannot: 8 records at
-    // a time, one per candidate; a launch offers at most 65536 * rows candidates, but the cap check drops, not wraps)
+    // the log takes the column candidates of ONE launch: about k per collecting row while chunks at most double (threads
+    // reserve it in segments of 8 records).  The cursor is 32 bits wide:
+    // the capacity stays below 2^31 records and a record past the capacity is dropped, not wrapped (the overflow flag
+    // sends the affected rows to the exact fallback)
     ix->col_log_cap = static_cast<uint32_t>(std::min<unsigned long long>(
         (1ull << 31) - (1ull << 24), std::max<unsigned long long>(1ull << 22, 2ull * n * static_cast<unsigned long long>(k))));
     TRY(ix->col_log.ensure(static_cast<size_t>(ix->col_log_cap) * 16));

@@ -20,7 +20,7 @@ except Exception:  # pragma: no cover
 def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, metric: str = "ip",
                         storage: str = "bf16", device: int = 0, chunk: int = 65536, index=None,
                         row_offset: int = 0, queries=None, query_groups=None, symmetric: bool = False,
-                        first_chunk: int = 8192):
+                        first_chunk: int = 65536):
     """Top-k most similar rows of `emb` for every row (or for `queries`), never
     returning the anchor row itself nor any row with the anchor's group id.
 
@@ -67,7 +67,7 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
     return np.concatenate(outs_d), np.concatenate(outs_i)
 
 
-def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 8192):
+def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 65536):
     """Anchor chunks of the symmetric self-join: (row0, rows) in row order.  Chunk 0 is the SEED region (handled by
     plain searches, cvdb_selfjoin_seed); every later chunk is at most as long as the rows before it (so a row's
     column buffer sees about k new candidates per chunk) and at most `chunk`."""
@@ -80,7 +80,7 @@ def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 8192):
 
 
 def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=None, chunk: int = 65536,
-                                  first_chunk: int = 8192, stats: Optional[dict] = None):
+                                  first_chunk: int = 65536, stats: Optional[dict] = None):
     """Self-join top-k over ALL rows of `index` (IP, bf16 storage, groups already set with set_groups) that computes
     every tile of X.X^T once and selects in both directions (include/cvdb_b200.h, cvdb_selfjoin_*): half the flops
     of mine_hard_negatives().  The first `first_chunk` rows are the seed (plain searches warm the column side up).
@@ -181,7 +181,7 @@ def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, 
 
 
 def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups=None, *, chunk: int = 65536,
-                                          first_chunk: int = 8192, stats: Optional[dict] = None):
+                                          first_chunk: int = 65536, stats: Optional[dict] = None):
     """The symmetric self-join over a ShardedIndex (one process per GPU, NCCL): every unordered pair of rows is
     scored once in the whole job.
 
