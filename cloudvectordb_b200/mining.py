@@ -20,7 +20,7 @@ except Exception:  # pragma: no cover
 def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, metric: str = "ip",
                         storage: str = "bf16", device: int = 0, chunk: int = 65536, index=None,
                         row_offset: int = 0, queries=None, query_groups=None, symmetric: bool = False,
-                        first_chunk: int = 65536):
+                        first_chunk: Optional[int] = None):
     """Top-k most similar rows of `emb` for every row (or for `queries`), never
     returning the anchor row itself nor any row with the anchor's group id.
 
@@ -67,6 +67,14 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
     return np.concatenate(outs_d), np.concatenate(outs_i)
 
 
+def default_seed_rows(n: int) -> int:
+    """Seed size of the symmetric self-join when the caller names none: about n/32 rows, a multiple of 8192 in
+    [8192, 65536].  The seed block is computed twice (plain searches in both directions) but at the full kernel
+    rate, while the first chunks after a small seed run at 0.1-0.5 of it (cold column lists); measured on one GPU:
+    2M rows 3.94 / 3.77 / 3.60 s and 6.25M rows - / 28.2 / 26.7 s with 8192 / 32768 / 65536 seed rows."""
+    return int(min(65536, max(8192, (n // 32 + 8191) // 8192 * 8192)))
+
+
 def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 65536):
     """Anchor chunks of the symmetric self-join: (row0, rows) in row order.  Chunk 0 is the SEED region (handled by
     plain searches, cvdb_selfjoin_seed); every later chunk is at most as long as the rows before it (so a row's
@@ -80,7 +88,7 @@ def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 65536):
 
 
 def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=None, chunk: int = 65536,
-                                  first_chunk: int = 65536, stats: Optional[dict] = None):
+                                  first_chunk: Optional[int] = None, stats: Optional[dict] = None):
     """Self-join top-k over ALL rows of `index` (IP, bf16 storage, groups already set with set_groups) that computes
     every tile of X.X^T once and selects in both directions (include/cvdb_b200.h, cvdb_selfjoin_*): half the flops
     of mine_hard_negatives().  The first `first_chunk` rows are the seed (plain searches warm the column side up).
@@ -90,6 +98,8 @@ def mine_hard_negatives_symmetric(index: IndexFlat, k: int, *, emb=None, groups=
     n = index.ntotal
     dev = torch.device("cuda", index.device)
     stream = int(torch.cuda.current_stream(index.device).cuda_stream)
+    if first_chunk is None:
+        first_chunk = default_seed_rows(n)
     if chunk % 256 or first_chunk % 256 or first_chunk > 65536:
         raise ValueError("chunk sizes must be multiples of 256 (the seed at most 65536)")
     _C.check(lib.cvdb_selfjoin_begin(index._h, int(k), stream))
@@ -181,7 +191,7 @@ def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, 
 
 
 def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups=None, *, chunk: int = 65536,
-                                          first_chunk: int = 65536, stats: Optional[dict] = None):
+                                          first_chunk: Optional[int] = None, stats: Optional[dict] = None):
     """The symmetric self-join over a ShardedIndex (one process per GPU, NCCL): every unordered pair of rows is
     scored once in the whole job.
 
@@ -189,10 +199,13 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     ONE of the two ranks computes it -- in both directions at once (cvdb_selfjoin_cross): the row direction gives
     the anchors of h their candidates among g's rows (sent back to h), the column direction gives g's rows their
     candidates among h's anchors (kept in g's column lists).  Rank g takes the anchors of the owners at distance
-    1 .. (G-1)/2 after it (mod G); with an even number of ranks the pair at distance G/2 is split by rows: the lower
-    rank computes (all anchors of the upper) x (its first half), the upper rank (second-half anchors of the lower) x
-    (all its rows).  The diagonal block is the single-GPU symmetric join (cvdb_selfjoin_chunk).  Every rank does
-    (G/2)/G of the plain job's flops.
+    1 .. (G-1)/2 after it (mod G).  With an even number of ranks the pair at distance G/2 is split like the diagonal
+    block, by chunk index, so that both ranks of the pair have the same work in every step (the all_to_all at the
+    end of a step makes ranks wait for each other): at step s each rank of the pair scores the OTHER rank's chunk s
+    against its own rows after its own chunk s, and one of the two (the upper rank at even steps, the lower at odd
+    ones) includes its chunk s as well -- a pair (a in chunk s of the lower, b in chunk t of the upper) is scored
+    on the upper rank when t > s, on the lower rank when t < s, and by that parity rule when t == s: exactly once.  The diagonal block is the single-GPU symmetric join
+    (cvdb_selfjoin_chunk).  Every rank does (G/2)/G of the plain job's flops.
 
     Steps.  All owners walk the same chunk schedule (selfjoin_schedule: a seed chunk handled by plain searches, then
     chunks that at most double); step s: all-gather chunk s of every
@@ -211,23 +224,31 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     bases = [sum(counts[:h]) for h in range(G)]
     n_loc, d = counts[g], int(local_emb.shape[1])
     stream = int(torch.cuda.current_stream(dev.index).cuda_stream)
+    if first_chunk is None:
+        first_chunk = default_seed_rows(max(counts))
     if chunk % 256 or first_chunk % 256 or first_chunk > 65536:
         raise ValueError("chunk sizes must be multiples of 256 (the seed at most 65536)")
     sched = [selfjoin_schedule(c, chunk, first_chunk) for c in counts]
     seed = [sc[0][1] if sc else 0 for sc in sched]       # rows [0, seed[h]) of shard h: handled by plain searches
     steps = max(len(sc) for sc in sched)
-    # the chunk boundary nearest to the middle of every shard (the row split of the distance-G/2 pairs)
-    half_idx = [min(range(len(sc)), key=lambda i: abs(sc[i][0] - c // 2)) if sc else 0 for sc, c in zip(sched, counts)]
-    half_row = [sc[i][0] if sc else 0 for sc, i in zip(sched, half_idx)]
     full_d = (G - 1) // 2
     has_groups = local_groups is not None
     grp_dev = local_groups.to(dev).to(torch.int32).contiguous() if has_groups else None
     _C.check(lib.cvdb_selfjoin_begin(local._h, int(k), stream))
     n_blocks = 0
+    marks = []   # (phase, event) pairs when the caller wants timings
+
+    def mark(name):
+        if stats is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+    mark("begin")
     try:
         row_keys = torch.zeros((n_loc, k), dtype=torch.int64, device=dev)
         if n_loc:   # column lists of my later rows start with their top-k among my seed anchors
             _C.check(lib.cvdb_selfjoin_seed(local._h, seed[g], bases[g], None, stream))
+        mark("seed_columns")
         for s_i in range(steps):
             ch = [sc[s_i] if s_i < len(sc) else (0, 0) for sc in sched]
             m_max = max(m for _, m in ch)
@@ -243,9 +264,11 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
             dist.all_gather_into_tensor(Q.view(G * m_max, d), q_mine, group=index.group)
             dist.all_gather_into_tensor(GR.view(-1), g_mine, group=index.group)
             send = torch.zeros((G, m_max, k), dtype=torch.int64, device=dev)
+            mark("gather")
             if m and s_i > 0:   # the diagonal block (chunk 0, the seed anchors, gets the plain sharded search below)
                 _C.check(lib.cvdb_selfjoin_chunk(local._h, r0, m, bases[g], send[g].data_ptr(), stream))
                 n_blocks += 1
+            mark("diagonal")
 
             def cross(h, row_begin, row_end):
                 hr0, hm = ch[h]
@@ -262,19 +285,21 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
 
             for dd in range(1, full_d + 1):
                 n_blocks += cross((g + dd) % G, 0, 0)
-            if G % 2 == 0 and G > 1:
+            if G % 2 == 0 and G > 1 and s_i < len(sched[g]):
+                # the distance-G/2 pair, split by chunk index (see the docstring)
                 h = (g + G // 2) % G
-                if g < h:                       # lower rank of the pair: every anchor chunk of h x my first half
-                    if half_row[g] > 0:
-                        n_blocks += cross(h, 0, half_row[g])
-                elif s_i >= half_idx[h]:        # upper rank: the second-half anchor chunks of h x all my rows
-                    n_blocks += cross(h, 0, 0)
+                begin = r0 if (g > h) == (s_i % 2 == 0) else r0 + m   # the chunk-s x chunk-s corner alternates
+                if begin < n_loc:
+                    n_blocks += cross(h, begin, 0)
+            mark("cross")
             recv = torch.empty_like(send)
             dist.all_to_all_single(recv.view(G * m_max, k), send.view(G * m_max, k), group=index.group)
+            mark("all_to_all")
             if m and s_i > 0:
                 merged = torch.empty((m_max, k), dtype=torch.int64, device=dev)
                 _C.check(lib.cvdb_merge_keys(recv.data_ptr(), m_max, G, k, k, merged.data_ptr(), stream))
                 row_keys[r0:r0 + m] = merged[:m]
+            mark("merge")
         D = torch.empty((n_loc, k), dtype=torch.float32, device=dev)
         I = torch.empty((n_loc, k), dtype=torch.int64, device=dev)
         max_dirty = max(1, min(n_loc, 1 << 22))
@@ -286,6 +311,7 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
         if n_loc:
             _C.check(lib.cvdb_selfjoin_dirty(local._h, rows.data_ptr(), max_dirty, _C.C.byref(nd), stream))
         del row_keys
+        mark("finish")
     finally:
         _C.check(lib.cvdb_selfjoin_end(local._h))
     # ---- rows that lost column candidates anywhere: recomputed by the plain sharded search, owner by owner
@@ -322,6 +348,13 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
             Dq, Iq = index.search(q, k, self_ids=ids, group_q=gq)
             if g == owner:
                 D[rr], I[rr] = Dq, Iq
+    if stats is not None:
+        mark("plain_rows")
+        torch.cuda.synchronize(dev)
+        phase_ms = {}
+        for (_, e0), (name, e1) in zip(marks, marks[1:]):
+            phase_ms[name] = phase_ms.get(name, 0.0) + e0.elapsed_time(e1)
+        stats["phase_ms"] = {n_: round(v, 2) for n_, v in phase_ms.items()}
     return D, I
 
 
