@@ -576,7 +576,8 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
     //       batches, exact-split storage, K > 768,
     //   2 = CTA pair with the queries resident on chip (bf16 storage, padded K <= 768; TMEM for the
     //       first 512 of K, shared-memory tail beyond; 128-column accumulators): large batches,
-    //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage),
+    //   3 = CTA pair streaming both operands (M = 256, N = 256; any K, any storage): short K with a real top-k, and
+    //       every batch of more than 128 queries the resident-query kernel cannot take (exact storage, K > 832),
     //   4 = CTA pair with all of K <= 768 in TMEM and 64-column accumulators (comparison only).
     const bool ts2_ok = ix->planes == 1 && p.nkb <= 13;  // padded K <= 832 (768 + the L2 norm columns)
     int variant = 1;
@@ -589,6 +590,12 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         if (p.nkb <= 2) variant = 1;
         else if (p.nkb <= 6 && k > 1) variant = 3;
         else variant = 2;
+    } else if (nq > 128) {
+        // exact (three-plane) storage or padded K > 832: the queries cannot stay resident, but the streaming CTA pair
+        // still fetches every database tile once per 256 queries.  tools/exact_variant_probe.py, variant 1 -> 3:
+        // configs[0] (100k x 384 exact, 10k queries) 3.68 -> 3.22 ms; 2M x 768 exact 152 -> 137 ms (10k queries),
+        // 4.4 -> 3.5 ms (256 queries); bf16 K = 1024 / 1536: 1180 -> 1360 TFLOP/s; identical results
+        variant = 3;
     }
     if (opts && opts->force_variant == 1) variant = 1;
     if (opts && opts->force_variant == 3) variant = 3;
