@@ -83,12 +83,18 @@ def test_slice_planner_properties():
         assert (s - 1) * tps < nt <= s * tps                      # the slices cover every tile, none is empty
         waves = math.ceil(qt * s / w)
         cost, cost_one = waves * (tps + 4), math.ceil(qt / w) * (nt + 4)
-        assert cost <= cost_one                                   # never worse than not slicing at all
+        assert cost <= 1.01 * cost_one                            # never (noticeably) worse than not slicing at all
         ideal = qt * nt / w
         if qt * nt >= 50 * w:
             assert cost <= 1.08 * ideal + 8                       # close to perfectly balanced for big problems
     # headline shape: 40 query tiles x 74 CTA pairs -> 37 slices, 20 whole waves
     assert plan(40, 78125, 74)[0] == 37
+    # long slices are avoided when a plan with shorter ones costs about the same: the mining chunk (256 query tiles of
+    # 256 anchors, 10M / 6.25M rows, at most 40 slices of scratch) takes slices of about 2000 tiles, not 13 long ones
+    for nt in (78125, 48829):
+        s, tps = plan(256, nt, 74, 40)
+        assert tps <= 2200 and s <= 40
+        assert math.ceil(256 * s / 74) * (tps + 8) <= 1.01 * 256 * nt / 74 + 8     # and stays balanced
     # a scratch budget caps the number of slices
     s, tps = plan(40, 78125, 74, 5)
     assert s <= 5 and (s - 1) * tps < 78125 <= s * tps
@@ -270,3 +276,19 @@ def test_sharded_mining_world2_gloo():
         assert not np.any(groups[I] == groups[lo:hi, None])
         seen += hi - lo
     assert seen == n
+
+
+def test_selfjoin_schedule_and_default_seed():
+    from cloudvectordb_b200.mining import default_seed_rows, selfjoin_schedule
+    for n in (1, 255, 1000, 70_000, 1_000_000, 2_000_000, 6_250_000, 50_000_000):
+        seed = default_seed_rows(n)
+        assert 8192 <= seed <= 65536 and seed % 8192 == 0
+        sched = selfjoin_schedule(n, 65536, seed)
+        assert sched[0] == (0, min(seed, n))
+        r = 0
+        for r0, m in sched:
+            assert r0 == r and 0 < m <= 65536 and (r0 == 0 or m <= r0)     # contiguous, in order, at most doubling
+            assert r0 % 256 == 0
+            r += m
+        assert r == n
+    assert default_seed_rows(1_000_000) == 32768 and default_seed_rows(6_250_000) == 65536
