@@ -646,8 +646,16 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         // shared thresholds [nq], wave counters [n_waves] and the per-item "flushed" counters [q_tiles * n_slices] live
         // in one buffer: one memset per launch
         const int64_t n_waves = ceil_div(n_items, std::min<int64_t>(workers, n_items));
-        TRY(ix->gthr.ensure(static_cast<size_t>(nq + n_waves + n_items) * 4));
-        CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, static_cast<size_t>(nq + n_waves + n_items) * 4, st));
+        // + the pooled per-slice order statistics (gemm_topk.cuh, "pooled thresholds"): worth it from 3 slices on and
+        // when an item is long enough for the 16-step publish chain at its end to vanish (debug flag 256: off)
+        const bool pool = E > 0 && E <= 16 && p.n_slices >= 3 &&
+                          (p.tiles_per_slice >= 128 || (opts && (opts->debug_flags & 512))) &&
+                          !(opts && (opts->debug_flags & (4 | 128 | 256)));
+        const size_t pool_off = (static_cast<size_t>(nq + n_waves + n_items) * 4 + 15) & ~size_t(15);  // uint4 loads
+        const size_t gthr_bytes = pool_off + (pool ? static_cast<size_t>(nq) * kPoolSlots * 4 : 0);
+        TRY(ix->gthr.ensure(gthr_bytes));
+        CU_TRY(cudaMemsetAsync(ix->gthr.p, 0, gthr_bytes, st));
+        p.gpool = pool ? reinterpret_cast<uint32_t*>(static_cast<char*>(ix->gthr.p) + pool_off) : nullptr;
         p.gthr = (opts && (opts->debug_flags & 4)) ? nullptr : ix->gthr.as<uint32_t>();
         p.wave_cnt = (opts && (opts->debug_flags & 8)) ? nullptr : ix->gthr.as<uint32_t>() + nq;
         // Optional (debug flag 128): a slice starts from the result of the latest finished earlier slice of its query

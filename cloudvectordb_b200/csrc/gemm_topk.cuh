@@ -113,6 +113,64 @@ __device__ __forceinline__ float publish_and_refresh(uint32_t* gq, uint64_t kth,
     return fmaxf(thr, t);
 }
 
+// POOLED THRESHOLDS across database slices.  gthr[q] only ever holds the best k-th score of a SINGLE slice, i.e. the
+// k-th best of ~rows/slices rows: with S slices every item still collects about k candidates per query (S*k in all,
+// where one running threshold over the whole database would collect ~k*ln(N/k)), and at k = 200 three of four 32x32
+// chunks took the slow path for that reason.  But finished slices say more than their k-th score: if m DIFFERENT
+// slices each hold ceil(k/m) rows scoring >= t, then k rows score >= t.  So every item also publishes, for
+// m = 2, 4, 8, 16, the score of rank ceil(k/m) of its result list into gpool[q] -- per level a list of the m largest
+// such values seen so far (kept by an atomicMax chain: each step keeps the larger value in the slot and carries the
+// smaller one down, so the slots always hold values of m distinct slices) -- and an item starts from the largest of
+// {gthr[q], min over the slots of every complete level}.  With 16 finished slices the bound is the rank-k/16 score
+// of a slice: about 16x fewer candidates per item.  Exact: only rows that provably cannot reach the global top-k
+// are filtered, equal scores still pass (thr_from_shared).  Off with slice inheritance (lists of different slices
+// then share rows) and for k = 1 (gthr is already exact).
+__device__ __forceinline__ float pooled_threshold(const uint32_t* __restrict__ g) {
+    uint32_t w[kPoolSlots];
+#pragma unroll
+    for (int i = 0; i < kPoolSlots / 4; ++i) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+    uint32_t best = 0;
+#pragma unroll
+    for (int m = 2; m <= 16; m <<= 1) {
+        uint32_t mn = 0xFFFFFFFFu;  // an empty slot (0) makes the level incomplete: min = 0
+#pragma unroll
+        for (int j = 0; j < m; ++j) mn = min(mn, w[m - 2 + j]);
+        best = max(best, mn);
+    }
+    return best != 0 ? thr_from_shared(best) : -INFINITY;
+}
+// lv[i] = score word at rank ceil(k / (2 << i)) of a sorted list held in registers (0: the list is shorter)
+template <int ES>
+__device__ __forceinline__ void pool_stats(const uint64_t (&key)[ES], int k, uint32_t (&lv)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = 2 << i;
+        const int pos = (k + m - 1) / m - 1;
+        lv[i] = pos < 32 * ES ? static_cast<uint32_t>(warp_sorted_at<ES>(key, pos) >> 32) : 0u;
+    }
+}
+// every lane: publish the order statistics `lv` of query `q` (q < 0: nothing to publish); the four levels' chains
+// are independent, so their atomics overlap
+__device__ __forceinline__ void pool_publish(uint32_t* __restrict__ gpool, int q, const uint32_t (&lv)[4]) {
+    if (q < 0) return;
+    uint32_t* g = gpool + static_cast<size_t>(q) * kPoolSlots;
+    uint32_t v[4] = {lv[0], lv[1], lv[2], lv[3]};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = 2 << i;
+            if (j < m && v[i] != 0) {
+                const uint32_t old = atomicMax(g + (m - 2) + j, v[i]);
+                v[i] = min(old, v[i]);
+            }
+        }
+    }
+}
+
 // Group exclusion (hard-negative mining: rows of the query's own group are not candidates).  Looking the group of
 // a row up while scanning would put an L2 round trip into the per-candidate path, so rows are collected
 // unchecked and the check runs here, on the whole buffer at once (the loads overlap), right before every sort;
@@ -346,6 +404,8 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
     // padding lanes (and, in a quartered small-batch tile, lanes that see another warp's query) never collect
     st.thr = !q_valid ? INFINITY : (st.gq ? thr_from_shared(__ldcg(st.gq)) : -INFINITY);
     if constexpr (E > 0) {
+        if (p.gpool != nullptr && q_valid)
+            st.thr = fmaxf(st.thr, pooled_threshold(p.gpool + static_cast<size_t>(q_row) * kPoolSlots));
         st.cnt = 0;
         int src = -1;
         if (E <= 16 && p.done != nullptr) {  // warp-uniform: every lane reads the same counters
@@ -394,7 +454,7 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
 // output entries.  Returns the k-th best key (0 when fewer than k candidates exist).
 template <int ES>
 __device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* out, int k, int grp,
-                                                 const int32_t* __restrict__ group_db) {
+                                                 const int32_t* __restrict__ group_db, uint32_t (&lv)[4]) {
     const int lane = threadIdx.x & 31;
     uint64_t key[ES];
 #pragma unroll
@@ -407,6 +467,7 @@ __device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* ou
         if (pos < k) out[pos] = key[e];
     }
     for (int pos = 32 * ES + lane; pos < k; pos += 32) out[pos] = 0;
+    pool_stats<ES>(key, k, lv);
     return k <= 32 * ES ? warp_sorted_at<ES>(key, k - 1) : 0;
 }
 
@@ -417,9 +478,12 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
     const uint32_t lane = threadIdx.x & 31;
     if constexpr (E > 0) {
         __syncwarp();
+        int pool_q = -1;                       // this lane's query and its order statistics for gpool
+        uint32_t pool_lv[4] = {0, 0, 0, 0};
         for (int l = 0; l < q_lanes; ++l) {
             const int qr = q_base + l;
             if (qr >= p.nq) break;
+            uint32_t lv[4] = {0, 0, 0, 0};
             uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
             uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
             const int grp_l = __shfl_sync(0xffffffffu, st.grp, l);
@@ -429,13 +493,13 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
                 // just the filled prefix then (32 slots cost a fifth of the 128-slot network of k = 50).
                 const int cnt_l = (p.dbg & 32) ? 32 * E : __shfl_sync(0xffffffffu, st.cnt, l);
                 if (E > 1 && cnt_l <= 32) {
-                    kth = flush_prefix<1>(b, out, p.k, grp_l, p.group_db);
+                    kth = flush_prefix<1>(b, out, p.k, grp_l, p.group_db, lv);
                 } else if (E > 2 && cnt_l <= 64) {
-                    kth = flush_prefix<2>(b, out, p.k, grp_l, p.group_db);
+                    kth = flush_prefix<2>(b, out, p.k, grp_l, p.group_db, lv);
                 } else if (E > 4 && cnt_l <= 128) {
-                    kth = flush_prefix<4>(b, out, p.k, grp_l, p.group_db);
+                    kth = flush_prefix<4>(b, out, p.k, grp_l, p.group_db, lv);
                 } else if (E > 8 && cnt_l <= 256) {
-                    kth = flush_prefix<8>(b, out, p.k, grp_l, p.group_db);
+                    kth = flush_prefix<8>(b, out, p.k, grp_l, p.group_db, lv);
                 } else {
                     uint64_t key[E];
                     kth = warp_compact<E>(b, p.k, key, grp_l, p.group_db);
@@ -444,6 +508,7 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
                         const int pos = e * 32 + lane;
                         if (pos < p.k) out[pos] = key[e];
                     }
+                    pool_stats<E>(key, p.k, lv);
                 }
             } else {
                 kth = warp_compact_mem<E>(b, p.k, grp_l, p.group_db);
@@ -451,7 +516,13 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
                     out[pos] = __ldcg(reinterpret_cast<const unsigned long long*>(b + pos));
             }
             if (static_cast<int>(lane) == l && kth != 0 && st.gq != nullptr) atomicMax(st.gq, static_cast<uint32_t>(kth >> 32));
+            if (static_cast<int>(lane) == l && st.gq != nullptr) {
+                pool_q = qr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pool_lv[i] = lv[i];
+            }
         }
+        if (p.gpool != nullptr) pool_publish(p.gpool, pool_q, pool_lv);   // all lanes at once: the chains overlap
         if (p.done != nullptr) {  // this warp's lists of the item are in part[]: later slices may start from them
             __threadfence();
             __syncwarp();
@@ -909,17 +980,18 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     uint64_t* b = warp_buf + static_cast<size_t>(l) * C;
                     uint64_t* out = p.part + static_cast<size_t>(dst_l) * p.k;
                     uint64_t kth;
+                    uint32_t lv_unused[4];  // (order statistics for the flat kernels' pooled thresholds)
                     if constexpr (E <= 16) {
                         // a list is a few hundred rows: most buffers hold a few dozen candidates
                         const int cnt_l = __shfl_sync(0xffffffffu, st.cnt, l);
                         if (E > 1 && cnt_l <= 32) {
-                            kth = flush_prefix<1>(b, out, p.k, -1, nullptr);
+                            kth = flush_prefix<1>(b, out, p.k, -1, nullptr, lv_unused);
                         } else if (E > 2 && cnt_l <= 64) {
-                            kth = flush_prefix<2>(b, out, p.k, -1, nullptr);
+                            kth = flush_prefix<2>(b, out, p.k, -1, nullptr, lv_unused);
                         } else if (E > 4 && cnt_l <= 128) {
-                            kth = flush_prefix<4>(b, out, p.k, -1, nullptr);
+                            kth = flush_prefix<4>(b, out, p.k, -1, nullptr, lv_unused);
                         } else if (E > 8 && cnt_l <= 256) {
-                            kth = flush_prefix<8>(b, out, p.k, -1, nullptr);
+                            kth = flush_prefix<8>(b, out, p.k, -1, nullptr, lv_unused);
                         } else {
                             uint64_t key[E];
                             kth = warp_compact<E>(b, p.k, key);

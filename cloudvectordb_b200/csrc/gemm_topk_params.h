@@ -6,6 +6,7 @@
 namespace cvdb {
 
 constexpr int kMaxCombos = 6;
+constexpr int kPoolSlots = 32;  // per query: levels m = 2, 4, 8, 16 at word offsets m - 2 (30 words used)
 
 struct GemmTopkParams {
     int nq;               // queries in this launch
@@ -28,6 +29,7 @@ struct GemmTopkParams {
     uint64_t* cand;  // [gridDim.x][128][32*E] candidate scratch (E>0)
     uint64_t* part;  // [nq][n_slices][k] per-slice results (keys)
     uint32_t* gthr;  // [nq] shared per-query threshold (ordered-float), zeroed before the launch
+    uint32_t* gpool;  // [nq][kPoolSlots] pooled per-slice order statistics (gemm_topk.cuh, "pooled thresholds"), zeroed; or null
     uint32_t* wave_cnt;  // [waves] producers that finished issuing the loads of their item in that wave (or null)
     uint32_t* done;      // [q_tiles][n_slices] epilogue warps that have flushed that item (zeroed; null: no inheritance)
     int done_full;       // warps that flush one item: 4 (single CTA) or 8 (CTA pair)

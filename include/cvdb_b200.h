@@ -77,8 +77,9 @@ typedef struct cvdb_search_opts {
                                 32 = always sort the whole candidate buffer at the end of a work item,
                                 64 = small batches: fill the query tile from row 0 up instead of one quarter per
                                 epilogue warp, 128 = every database slice starts from the result list of the latest finished
-                                earlier slice of its query tile instead of an empty candidate buffer (4, 8, 16, 32, 64
-                                and 128 leave the results valid) */
+                                earlier slice of its query tile instead of an empty candidate buffer, 256 = no pooled
+                                thresholds across slices, 512 = pooled thresholds also for short work items (4, 8, 16,
+                                32, 64, 128, 256 and 512 leave the results valid) */
 } cvdb_search_opts;
 
 /* -- index lifetime -------------------------------------------------------

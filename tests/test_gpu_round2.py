@@ -313,3 +313,45 @@ def test_slice_inheritance_is_result_neutral(variant, k):
     D_ref, I_ref = O.search_ref(xb, xb[self_ids], k, O.METRIC_IP, self_ids=self_ids, group_db=groups, group_q=gq)
     assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
     idx.close()
+
+
+# ---- pooled thresholds across slices (order statistics of finished slices bound what later slices collect) ------
+@pytest.mark.parametrize("variant,k,metric", [(1, 10, "ip"), (2, 50, "ip"), (3, 100, "ip"), (2, 200, "ip"), (1, 3, "l2"),
+                                              (2, 17, "l2"), (3, 248, "ip")])
+def test_pooled_thresholds_are_result_neutral(variant, k, metric):
+    """Many slices, pooled thresholds forced on for short items (debug flag 512): identical to the run without them
+    (flag 256) and equal to the oracle -- on iid rows, with blocks of exact duplicates spread over slices (ties at the
+    k-th score must survive the pooled bound), on rows sorted by ASCENDING score (every slice beats all earlier
+    ones) and DESCENDING score (the first slices already hold the answer), and with self + group exclusion."""
+    from cloudvectordb_b200 import IndexFlat
+    rng = np.random.default_rng(variant * 1000 + k)
+    n, d, nq = 300_000, 64, 200
+    code = O.METRIC_IP if metric == "ip" else O.METRIC_L2
+    xb = O.bf16_round(unit_rows(rng, n, d))
+    for r0 in (500, 60_000, 150_000, 299_000):                 # the same row in many slices: ties across slices
+        xb[r0:r0 + 70] = xb[3]
+    xq = O.bf16_round(unit_rows(rng, nq, d))
+    xq[0] = xb[3]
+    slices = 37 if variant != 1 else 41
+    for order in ("iid", "ascending", "descending"):
+        if order != "iid":
+            s = xb @ xq[1]
+            xb = xb[np.argsort(s if order == "ascending" else -s, kind="stable")]
+        idx = IndexFlat(d, metric, "bf16", 0)
+        idx.add(xb)
+        D, I = idx.search(xq, k, force_variant=variant, force_slices=slices, debug_flags=512)
+        assert idx.last_work()["n_slices"] >= 33
+        D0, I0 = idx.search(xq, k, force_variant=variant, force_slices=slices, debug_flags=256)
+        assert np.array_equal(I, I0) and np.array_equal(D, D0), order
+        D_ref, I_ref = O.search_ref(xb, xq, k, code)
+        assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5, metric=code) == 0, order
+        if order == "iid" and metric == "ip":
+            groups = (np.arange(n) // 4).astype(np.int32)
+            idx.set_groups(groups)
+            self_ids = rng.integers(0, n, nq).astype(np.int32)
+            gq = groups[self_ids]
+            D, I = idx.search(xb[self_ids], k, self_ids=self_ids, group_q=gq, force_variant=variant, force_slices=slices,
+                              debug_flags=512)
+            D_ref, I_ref = O.search_ref(xb, xb[self_ids], k, O.METRIC_IP, self_ids=self_ids, group_db=groups, group_q=gq)
+            assert O.check_topk(D, I, D_ref, I_ref, tie_tol=2e-5) == 0
+        idx.close()
