@@ -118,7 +118,7 @@ __device__ __forceinline__ float publish_and_refresh(uint32_t* gq, uint64_t kth,
 // where one running threshold over the whole database would collect ~k*ln(N/k)), and at k = 200 three of four 32x32
 // chunks took the slow path for that reason.  But finished slices say more than their k-th score: if m DIFFERENT
 // slices each hold ceil(k/m) rows scoring >= t, then k rows score >= t.  So every item also publishes, for
-// m = 2, 4, 8, 16, the score of rank ceil(k/m) of its result list into gpool[q] -- per level a list of the m largest
+// m = 2, 4, 8, 16 (kPoolLevels), the score of rank ceil(k/m) of its result list into gpool[q] -- per level a list of the m largest
 // such values seen so far (kept by an atomicMax chain: each step keeps the larger value in the slot and carries the
 // smaller one down, so the slots always hold values of m distinct slices) -- and an item starts from the largest of
 // {gthr[q], min over the slots of every complete level}.  With 16 finished slices the bound is the rank-k/16 score
@@ -134,7 +134,7 @@ __device__ __forceinline__ float pooled_threshold(const uint32_t* __restrict__ g
     }
     uint32_t best = 0;
 #pragma unroll
-    for (int m = 2; m <= 16; m <<= 1) {
+    for (int m = 2; m <= (1 << kPoolLevels); m <<= 1) {
         uint32_t mn = 0xFFFFFFFFu;  // an empty slot (0) makes the level incomplete: min = 0
 #pragma unroll
         for (int j = 0; j < m; ++j) mn = min(mn, w[m - 2 + j]);
@@ -144,9 +144,9 @@ __device__ __forceinline__ float pooled_threshold(const uint32_t* __restrict__ g
 }
 // lv[i] = score word at rank ceil(k / (2 << i)) of a sorted list held in registers (0: the list is shorter)
 template <int ES>
-__device__ __forceinline__ void pool_stats(const uint64_t (&key)[ES], int k, uint32_t (&lv)[4]) {
+__device__ __forceinline__ void pool_stats(const uint64_t (&key)[ES], int k, uint32_t (&lv)[kPoolLevels]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPoolLevels; ++i) {
         const int m = 2 << i;
         const int pos = (k + m - 1) / m - 1;
         lv[i] = pos < 32 * ES ? static_cast<uint32_t>(warp_sorted_at<ES>(key, pos) >> 32) : 0u;
@@ -154,14 +154,16 @@ __device__ __forceinline__ void pool_stats(const uint64_t (&key)[ES], int k, uin
 }
 // every lane: publish the order statistics `lv` of query `q` (q < 0: nothing to publish); the four levels' chains
 // are independent, so their atomics overlap
-__device__ __forceinline__ void pool_publish(uint32_t* __restrict__ gpool, int q, const uint32_t (&lv)[4]) {
+__device__ __forceinline__ void pool_publish(uint32_t* __restrict__ gpool, int q, const uint32_t (&lv)[kPoolLevels]) {
     if (q < 0) return;
     uint32_t* g = gpool + static_cast<size_t>(q) * kPoolSlots;
-    uint32_t v[4] = {lv[0], lv[1], lv[2], lv[3]};
+    uint32_t v[kPoolLevels];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int i = 0; i < kPoolLevels; ++i) v[i] = lv[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < (1 << kPoolLevels); ++j) {
+#pragma unroll
+        for (int i = 0; i < kPoolLevels; ++i) {
             const int m = 2 << i;
             if (j < m && v[i] != 0) {
                 const uint32_t old = atomicMax(g + (m - 2) + j, v[i]);
@@ -454,7 +456,7 @@ __device__ __forceinline__ void item_begin(LaneTopk<E>& st, const GemmTopkParams
 // output entries.  Returns the k-th best key (0 when fewer than k candidates exist).
 template <int ES>
 __device__ __forceinline__ uint64_t flush_prefix(const uint64_t* b, uint64_t* out, int k, int grp,
-                                                 const int32_t* __restrict__ group_db, uint32_t (&lv)[4]) {
+                                                 const int32_t* __restrict__ group_db, uint32_t (&lv)[kPoolLevels]) {
     const int lane = threadIdx.x & 31;
     uint64_t key[ES];
 #pragma unroll
@@ -479,11 +481,11 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
     if constexpr (E > 0) {
         __syncwarp();
         int pool_q = -1;                       // this lane's query and its order statistics for gpool
-        uint32_t pool_lv[4] = {0, 0, 0, 0};
+        uint32_t pool_lv[kPoolLevels] = {};
         for (int l = 0; l < q_lanes; ++l) {
             const int qr = q_base + l;
             if (qr >= p.nq) break;
-            uint32_t lv[4] = {0, 0, 0, 0};
+            uint32_t lv[kPoolLevels] = {};
             uint64_t* b = reinterpret_cast<uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(st.buf), l));
             uint64_t* out = p.part + (static_cast<size_t>(qr) * p.n_slices + slice) * p.k;
             const int grp_l = __shfl_sync(0xffffffffu, st.grp, l);
@@ -519,7 +521,7 @@ __device__ __forceinline__ void item_flush(LaneTopk<E>& st, const GemmTopkParams
             if (static_cast<int>(lane) == l && st.gq != nullptr) {
                 pool_q = qr;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) pool_lv[i] = lv[i];
+                for (int i = 0; i < kPoolLevels; ++i) pool_lv[i] = lv[i];
             }
         }
         if (p.gpool != nullptr) pool_publish(p.gpool, pool_q, pool_lv);   // all lanes at once: the chains overlap
@@ -980,7 +982,7 @@ gemm_topk_grouped_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     uint64_t* b = warp_buf + static_cast<size_t>(l) * C;
                     uint64_t* out = p.part + static_cast<size_t>(dst_l) * p.k;
                     uint64_t kth;
-                    uint32_t lv_unused[4];  // (order statistics for the flat kernels' pooled thresholds)
+                    uint32_t lv_unused[kPoolLevels];  // (order statistics for the flat kernels' pooled thresholds)
                     if constexpr (E <= 16) {
                         // a list is a few hundred rows: most buffers hold a few dozen candidates
                         const int cnt_l = __shfl_sync(0xffffffffu, st.cnt, l);

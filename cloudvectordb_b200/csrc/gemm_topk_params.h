@@ -6,7 +6,12 @@
 namespace cvdb {
 
 constexpr int kMaxCombos = 6;
-constexpr int kPoolSlots = 32;  // per query: levels m = 2, 4, 8, 16 at word offsets m - 2 (30 words used)
+// pooled thresholds (gemm_topk.cuh): levels m = 2, 4, .., 2^kPoolLevels; level m keeps m words at word offset m - 2
+#ifndef CVDB_POOL_LEVELS
+#define CVDB_POOL_LEVELS 4
+#endif
+constexpr int kPoolLevels = CVDB_POOL_LEVELS;
+constexpr int kPoolSlots = 2 << kPoolLevels;  // 32 words per query for 4 levels (30 used)
 
 struct GemmTopkParams {
     int nq;               // queries in this launch
