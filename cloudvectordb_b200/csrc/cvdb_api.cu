@@ -648,8 +648,9 @@ int search_device(Index* ix, const void* q_dev, int64_t nq, int dtype, int k, fl
         const int64_t n_waves = ceil_div(n_items, std::min<int64_t>(workers, n_items));
         // + the pooled per-slice order statistics (gemm_topk.cuh, "pooled thresholds"): worth it from 3 slices on and
         // when an item is long enough for the 16-step publish chain at its end to vanish (debug flag 256: off)
+        // (a launch of a single wave -- small HBM-bound batches -- has nobody to publish to: all items start together)
         const bool pool = E > 0 && E <= 16 && p.n_slices >= 3 &&
-                          (p.tiles_per_slice >= 128 || (opts && (opts->debug_flags & 512))) &&
+                          ((p.tiles_per_slice >= 128 && n_waves > 1) || (opts && (opts->debug_flags & 512))) &&
                           !(opts && (opts->debug_flags & (4 | 128 | 256)));
         const size_t pool_off = (static_cast<size_t>(nq + n_waves + n_items) * 4 + 15) & ~size_t(15);  // uint4 loads
         const size_t gthr_bytes = pool_off + (pool ? static_cast<size_t>(nq) * kPoolSlots * 4 : 0);

@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")/.."
 B=cloudvectordb_b200/csrc/build
-for f in k_ss1 k_ss2 k_grouped k_ivf_scan k_ts2_cfg0 k_ts2_cfg1 k_ts2_cfg2 k_ts2_cfg3 cvdb_api; do
+for f in k_ss1 k_ss2 k_grouped k_ivf_scan k_ts2 k_ts2_cfg0 k_ts2_cfg1 k_ts2_cfg2 k_ts2_cfg3 k_ts2_col cvdb_api; do
   [ -f $B/$f.o ] || continue
   out=profiles/sass_opcodes_$f.txt
   {
