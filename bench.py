@@ -406,12 +406,17 @@ def run_ours(a):
     # dominant kernel roofline (tensor-bound: 2*nq*rows_local*d flops per launch)
     w = local.last_work()
     kernel_ms = float(np.mean(kms))
+    kernel_ms_by_rank = [kernel_ms]
+    if world > 1:   # rank skew: a step ends when the slowest rank's all-gather completes
+        kernel_ms_by_rank = [None] * world
+        dist.all_gather_object(kernel_ms_by_rank, kernel_ms)
     achieved = w["flops"] / kernel_ms / 1e9
     roofline = {"bound": "tensor", "kernel": "gemm_topk", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "peak_kind": "sustained cuBLAS bf16, " + peaks["source"],
                 "peak_burst": peaks["bf16_tflops"], "frac_burst": achieved / peaks["bf16_tflops"],
                 "frac_nominal_2250": achieved / 2250.0, "kernel_ms": kernel_ms,
-                "kernel_share_of_step": kernel_ms / ms_per_step, "flops_per_launch": w["flops"],
+                "kernel_share_of_step": kernel_ms / ms_per_step, "kernel_ms_by_rank": kernel_ms_by_rank,
+                "slowest_rank_kernel_share_of_step": max(kernel_ms_by_rank) / ms_per_step, "flops_per_launch": w["flops"],
                 "db_bytes_per_launch": w["db_bytes"], "hbm_gbs_algorithmic": w["db_bytes"] / kernel_ms / 1e6,
                 "traffic": measured_traffic(world),
                 "traffic_note": "dram bytes per launch from an ncu --set full capture of this N (profiles/roofline_traffic.json); "
