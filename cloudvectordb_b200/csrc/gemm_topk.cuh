@@ -1357,7 +1357,15 @@ gemm_topk_ts2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 if (p.q_ids != nullptr && q_valid) anchor_id = static_cast<uint32_t>(__ldg(p.q_ids + q_row));
             }
             // column direction: the thresholds of a tile's database rows (lane l: columns l, l+32, ...), fetched one
-            // tile ahead so the L2 round trip never sits between an accumulator becoming ready and its scan
+            // tile ahead so the L2 round trip never sits between an accumulator becoming ready and its scan.
+            // Tried on the 6.25M-row join and dropped (same-box A/B against this version, 25.2-25.4 s):
+            //  * a precomputed per-tile minimum of the thresholds (one broadcast load per tile, row thresholds only
+            //    fetched when a chunk beats it): 25.3-25.5 s, no gain;
+            //  * deciding once per TILE (accumulate the chunk maxima, one vote, re-read the accumulator from tensor
+            //    memory for the rare tile that fires): the accumulator has to be kept until the decision, and that
+            //    later hand-off to the MMA warp cost more than the three votes saved: 26.4 s;
+            //  * issuing the tensor-memory load of the next 32 columns before scanning the current 32 (two register
+            //    sets, +35 registers): 29.1 s, and k = 200 on the headline shape 91.5k -> 88.8k qps.
             float cthr_next[COL ? BLOCK_N / 32 : 1];
             auto load_cthr = [&](int t, float (&out)[COL ? BLOCK_N / 32 : 1]) {
 #pragma unroll
