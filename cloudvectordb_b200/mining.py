@@ -68,11 +68,12 @@ def mine_hard_negatives(emb, k: int, groups=None, *, exclude_self: bool = True, 
 
 
 def default_seed_rows(n: int) -> int:
-    """Seed size of the symmetric self-join when the caller names none: about n/32 rows, a multiple of 8192 in
-    [8192, 65536].  The seed block is computed twice (plain searches in both directions) but at the full kernel
-    rate, while the first chunks after a small seed run at 0.1-0.5 of it (cold column lists); measured on one GPU:
-    2M rows 3.94 / 3.77 / 3.60 s and 6.25M rows - / 28.2 / 26.7 s with 8192 / 32768 / 65536 seed rows."""
-    return int(min(65536, max(8192, (n // 32 + 8191) // 8192 * 8192)))
+    """Seed size of the symmetric self-join when the caller names none: 65 536 rows (the largest the C ABI takes).
+    The seed block is computed twice (plain searches in both directions) but at the full kernel rate, while the first
+    chunks after a small seed run at 0.1-0.5 of it (cold column lists).  Measured: one GPU, 2M rows 3.94 / 3.77 /
+    3.60 s and 6.25M rows - / 28.2 / 26.7 s with 8192 / 32768 / 65536 seed rows; two GPUs, 1M rows each: 2.64 s with
+    32768 against 2.09 s with 65536.  (Corpora smaller than the seed are joined by the plain searches alone.)"""
+    return 65536
 
 
 def selfjoin_schedule(n: int, chunk: int = 65536, first: int = 65536):

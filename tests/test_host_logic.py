@@ -282,7 +282,7 @@ def test_selfjoin_schedule_and_default_seed():
     from cloudvectordb_b200.mining import default_seed_rows, selfjoin_schedule
     for n in (1, 255, 1000, 70_000, 1_000_000, 2_000_000, 6_250_000, 50_000_000):
         seed = default_seed_rows(n)
-        assert 8192 <= seed <= 65536 and seed % 8192 == 0
+        assert seed == 65536
         sched = selfjoin_schedule(n, 65536, seed)
         assert sched[0] == (0, min(seed, n))
         r = 0
@@ -291,4 +291,3 @@ def test_selfjoin_schedule_and_default_seed():
             assert r0 % 256 == 0
             r += m
         assert r == n
-    assert default_seed_rows(1_000_000) == 32768 and default_seed_rows(6_250_000) == 65536
