@@ -530,33 +530,48 @@ __global__ void col_compact_kernel(uint64_t* __restrict__ col_buf, uint32_t* __r
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t r = row_min + warp0; r < n_rows; r += nwarps) {
-        const uint32_t cnt = col_cnt[r];
-        if (cnt == col_base[r]) continue;  // nothing new (warp-uniform)
-        if (cnt > static_cast<uint32_t>(kColCap)) {
-            if (lane == 0) {
-                dirty[r] = 1;
-                col_thr[r] = INFINITY;
-                col_base[r] = cnt;
+    // A warp takes 32 consecutive rows at a time: every lane looks at one row's counters (coalesced), then the rows
+    // that did receive candidates are compacted one after the other by the whole warp.  (Measured on a steady-state
+    // chunk of the 6.25M-row join: 2.2 ms per chunk either way -- about two thirds of the rows receive a candidate per
+    // chunk, so the selects themselves are the cost: 0.9 % of the chunk.)
+    for (int64_t r0 = row_min + warp0 * 32; r0 < n_rows; r0 += nwarps * 32) {
+        const int64_t rl = r0 + lane;
+        uint32_t cnt_l = 0, base_l = 0;
+        if (rl < n_rows) {
+            cnt_l = col_cnt[rl];
+            base_l = col_base[rl];
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, cnt_l != base_l);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t r = r0 + l;
+            const uint32_t cnt = __shfl_sync(0xffffffffu, cnt_l, l);
+            if (cnt > static_cast<uint32_t>(kColCap)) {
+                if (lane == 0) {
+                    dirty[r] = 1;
+                    col_thr[r] = INFINITY;
+                    col_base[r] = cnt;
+                }
+                continue;
             }
-            continue;
-        }
-        uint64_t* b = col_buf + r * kColCap;
-        uint64_t key[E];
+            uint64_t* b = col_buf + r * kColCap;
+            uint64_t key[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const uint32_t pos = e * 32 + lane;
-            key[e] = pos < cnt ? b[pos] : 0;
-        }
-        uint64_t kth;
-        const uint64_t T = warp_select_threshold<E>(key, k, kth);
-        const int kept = warp_store_survivors<E>(b, key, T);
-        if (lane == 0) {
-            col_cnt[r] = kept;
-            col_base[r] = kept;
-            const uint32_t ord = static_cast<uint32_t>(kth >> 32);
-            // equal scores stay candidates (the key decides): one step below the k-th score
-            if (ord != 0) col_thr[r] = ord == 0x80000000u ? -1.17549435e-38f : ordered_to_float(ord - 1u);
+            for (int e = 0; e < E; ++e) {
+                const uint32_t pos = e * 32 + lane;
+                key[e] = pos < cnt ? b[pos] : 0;
+            }
+            uint64_t kth;
+            const uint64_t T = warp_select_threshold<E>(key, k, kth);
+            const int kept = warp_store_survivors<E>(b, key, T);
+            if (lane == 0) {
+                col_cnt[r] = kept;
+                col_base[r] = kept;
+                const uint32_t ord = static_cast<uint32_t>(kth >> 32);
+                // equal scores stay candidates (the key decides): one step below the k-th score
+                if (ord != 0) col_thr[r] = ord == 0x80000000u ? -1.17549435e-38f : ordered_to_float(ord - 1u);
+            }
         }
     }
 }

@@ -1453,7 +1453,7 @@ int selfjoin_compact(Index* ix, int64_t row_min, int64_t row_end, cudaStream_t s
     g_launches += 2;
     CU_TRY(cudaGetLastError());
     if (row_min >= row_end) return CVDB_OK;
-    const int64_t blocks = std::min<int64_t>(ceil_div(row_end - row_min, 8), 148 * 32);
+    const int64_t blocks = std::min<int64_t>(ceil_div(row_end - row_min, 8 * 32), 148 * 32);  // a warp per 32 rows
     col_compact_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ix->col_buf.as<uint64_t>(), ix->col_cnt.as<uint32_t>(),
                                                                       ix->col_base.as<uint32_t>(), ix->col_thr.as<float>(),
                                                                       ix->col_dirty.as<uint8_t>(), ix->sj_k, row_min, row_end);
