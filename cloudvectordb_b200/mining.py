@@ -191,6 +191,45 @@ def mine_hard_negatives_sharded(index, local_emb, k: int, local_groups=None, *, 
     return torch.cat(outs_d), torch.cat(outs_i)
 
 
+def selfjoin_block_plan(counts, chunk: int = 65536, first_chunk: int = 65536):
+    """Host-side plan of the sharded symmetric self-join (pure function of the shard sizes; no GPU needed).
+
+    Returns (sched, plan): sched[h] is shard h's chunk schedule (selfjoin_schedule), plan[s][g] the cross blocks rank
+    g computes at step s as (h, row_begin) tuples: the anchors are chunk s of shard h, the database rows are rows
+    [row_begin, counts[g]) of shard g, both directions at once.  The diagonal blocks (shard g's own chunks) are not
+    listed.  Every unordered pair of rows from two different shards is covered by exactly one block of the plan
+    (tests/test_host_logic.py enumerates this for 1..8 ranks and uneven shards); see
+    mine_hard_negatives_sharded_symmetric for the rule."""
+    G = len(counts)
+    sched = [selfjoin_schedule(c, chunk, first_chunk) for c in counts]
+    steps = max((len(sc) for sc in sched), default=0)
+    full_d = (G - 1) // 2
+    plan = []
+    for s_i in range(steps):
+        ch = [sc[s_i] if s_i < len(sc) else (0, 0) for sc in sched]
+        row = []
+        for g in range(G):
+            blocks = []
+            r0, m = ch[g]
+
+            def want(h):
+                return ch[h][1] > 0 and counts[g] > 0
+
+            for dd in range(1, full_d + 1):
+                h = (g + dd) % G
+                if want(h):
+                    blocks.append((h, 0))
+            if G % 2 == 0 and G > 1 and s_i < len(sched[g]):
+                # the distance-G/2 pair, split by chunk index (the chunk-s x chunk-s corner alternates)
+                h = (g + G // 2) % G
+                begin = r0 if (g > h) == (s_i % 2 == 0) else r0 + m
+                if begin < counts[g] and want(h):
+                    blocks.append((h, begin))
+            row.append(blocks)
+        plan.append(row)
+    return sched, plan
+
+
 def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups=None, *, chunk: int = 65536,
                                           first_chunk: Optional[int] = None, stats: Optional[dict] = None):
     """The symmetric self-join over a ShardedIndex (one process per GPU, NCCL): every unordered pair of rows is
@@ -205,8 +244,9 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
     end of a step makes ranks wait for each other): at step s each rank of the pair scores the OTHER rank's chunk s
     against its own rows after its own chunk s, and one of the two (the upper rank at even steps, the lower at odd
     ones) includes its chunk s as well -- a pair (a in chunk s of the lower, b in chunk t of the upper) is scored
-    on the upper rank when t > s, on the lower rank when t < s, and by that parity rule when t == s: exactly once.  The diagonal block is the single-GPU symmetric join
-    (cvdb_selfjoin_chunk).  Every rank does (G/2)/G of the plain job's flops.
+    on the upper rank when t > s, on the lower rank when t < s, and by that parity rule when t == s: exactly once.
+    The diagonal block is the single-GPU symmetric join (cvdb_selfjoin_chunk).  Every rank does (G/2)/G of the plain
+    job's flops.  The plan itself is selfjoin_block_plan (a pure function, checked exhaustively on CPU).
 
     Steps.  All owners walk the same chunk schedule (selfjoin_schedule: a seed chunk handled by plain searches, then
     chunks that at most double); step s: all-gather chunk s of every
@@ -229,10 +269,9 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
         first_chunk = default_seed_rows(max(counts))
     if chunk % 256 or first_chunk % 256 or first_chunk > 65536:
         raise ValueError("chunk sizes must be multiples of 256 (the seed at most 65536)")
-    sched = [selfjoin_schedule(c, chunk, first_chunk) for c in counts]
+    sched, plan = selfjoin_block_plan(counts, chunk, first_chunk)
     seed = [sc[0][1] if sc else 0 for sc in sched]       # rows [0, seed[h]) of shard h: handled by plain searches
-    steps = max(len(sc) for sc in sched)
-    full_d = (G - 1) // 2
+    steps = len(plan)
     has_groups = local_groups is not None
     grp_dev = local_groups.to(dev).to(torch.int32).contiguous() if has_groups else None
     _C.check(lib.cvdb_selfjoin_begin(local._h, int(k), stream))
@@ -284,14 +323,8 @@ def mine_hard_negatives_sharded_symmetric(index, local_emb, k: int, local_groups
                                                  seed[g], bases[g], send[h].data_ptr(), stream))
                 return 1
 
-            for dd in range(1, full_d + 1):
-                n_blocks += cross((g + dd) % G, 0, 0)
-            if G % 2 == 0 and G > 1 and s_i < len(sched[g]):
-                # the distance-G/2 pair, split by chunk index (see the docstring)
-                h = (g + G // 2) % G
-                begin = r0 if (g > h) == (s_i % 2 == 0) else r0 + m   # the chunk-s x chunk-s corner alternates
-                if begin < n_loc:
-                    n_blocks += cross(h, begin, 0)
+            for h, begin in plan[s_i][g]:
+                n_blocks += cross(h, begin, 0)
             mark("cross")
             recv = torch.empty_like(send)
             dist.all_to_all_single(recv.view(G * m_max, k), send.view(G * m_max, k), group=index.group)

@@ -291,3 +291,39 @@ def test_selfjoin_schedule_and_default_seed():
             assert r0 % 256 == 0
             r += m
         assert r == n
+
+
+def test_sharded_symmetric_join_plan_covers_every_cross_shard_pair_exactly_once():
+    """The block plan of the sharded symmetric self-join (mining.selfjoin_block_plan): block (h, begin) of rank g at
+    step s scores the anchors of chunk s of shard h against rows [begin, n_g) of shard g in BOTH directions.  Over all
+    steps and ranks every unordered pair of rows from two different shards must be scored exactly once, for odd and
+    even rank counts, uneven and empty shards, ragged last chunks and shards with different numbers of chunks; and
+    the ranks' work per step must be balanced for equal shards."""
+    import itertools
+    from cloudvectordb_b200.mining import selfjoin_block_plan
+    cases = [([1024], 256, 256), ([1024, 1024], 256, 256), ([1000, 700], 256, 256), ([700, 1000], 256, 512),
+             ([1024, 1024, 1024], 256, 256), ([900, 300, 1500], 256, 256), ([512, 512, 512, 512], 256, 256),
+             ([1500, 260, 777, 1024], 256, 256), ([600, 0, 900, 300], 256, 256), ([640] * 5, 256, 256),
+             ([400, 800, 1200, 300, 650, 1024], 256, 256), ([768] * 8, 256, 256), ([2048] * 8, 512, 256),
+             ([300, 1300, 700, 256, 1024, 513, 900, 1100], 256, 256)]
+    for counts, chunk, first in cases:
+        G = len(counts)
+        sched, plan = selfjoin_block_plan(counts, chunk, first)
+        cover = {(a, b): np.zeros((counts[a], counts[b]), np.int32) for a, b in itertools.combinations(range(G), 2)}
+        work = np.zeros((len(plan), G))
+        for s_i, row in enumerate(plan):
+            for g, blocks in enumerate(row):
+                for h, begin in blocks:
+                    assert h != g and begin % 128 == 0 and 0 <= begin < counts[g]
+                    hr0, hm = sched[h][s_i]
+                    assert hm > 0
+                    work[s_i, g] += hm * (counts[g] - begin)
+                    if h < g:
+                        cover[(h, g)][hr0:hr0 + hm, begin:] += 1
+                    else:
+                        cover[(g, h)][begin:, hr0:hr0 + hm] += 1
+        for (a, b), c in cover.items():
+            assert (c == 1).all(), (counts, a, b, int(c.min()), int(c.max()))
+        if len(set(counts)) == 1 and G > 1:      # equal shards: no rank waits for another inside a step
+            for s_i in range(len(plan)):
+                assert work[s_i].max() - work[s_i].min() <= chunk * chunk, (counts, s_i, work[s_i])
