@@ -43,8 +43,10 @@ def test_schedule_covers_rows_in_order_and_at_most_doubles():
     (6_001, 96, 100, 65536, 256),    # ragged size, k = 100
     (3_000, 40, 2, 256, 256),        # smallest k, smallest chunks
     (700, 32, 20, 65536, 256),       # fewer rows than three chunks
-    (30_000, 64, 10, 8192, 8192),    # the default seed size
+    (30_000, 64, 10, 8192, 8192),    # a seed of 8192 rows
     (5_000, 64, 10, 65536, 8192),    # the seed covers every row: all plain
+    (70_000, 64, 10, 65536, None),   # the default seed (65 536 rows) and one short chunk after it
+    (4_000, 48, 12, 65536, None),    # default seed larger than the corpus
 ])
 def test_symmetric_join_equals_plain_join_and_oracle(n, d, k, chunk, first):
     from cloudvectordb_b200 import mine_hard_negatives
