@@ -57,7 +57,7 @@ def main(argv=None):
         flat.set_groups(groups)
         # self-join, anchor + positives excluded; symmetric=True scores every pair of rows once (both directions are
         # selected from the same tile), about 0.6 of the plain join's time on millions of rows
-        D, I = mine_hard_negatives(emb, a.k, groups, index=flat, symmetric=a.k <= 124)
+        D, I = mine_hard_negatives(emb, a.k, groups, index=flat, symmetric=(2 <= a.k <= 124 and a.dim <= 768))
         positives = torch.where(torch.arange(n, device=dev) % a.group_size == 0, torch.arange(n, device=dev) + 1,
                                 torch.arange(n, device=dev) - 1).clamp(max=n - 1)
         T = build_triplets(D, I, positives, skip_top=1, per_anchor=4, limit=0.95)
